@@ -1,0 +1,471 @@
+// CSR x dense SpMM for the GCN propagation hot path (sm_100a).
+//
+// Replaces S.dot(H, activation) / S.dot(input, W) of lasagne_layers.py:26,65,67,84
+// and, through A_hat^T = A_hat and a pre-transposed X, their gradients.
+//
+// Layout / algorithm
+//   * A "group" of G lanes (G in {4,8,16,32}) owns one output row inside one
+//     column panel; each lane keeps VPL float4 accumulators, so a panel is
+//     4*G*VPL floats wide.  Lanes of a group read G*16 contiguous bytes of the
+//     gathered dense row per load -> fully coalesced 128-bit loads.
+//   * Column indices / values are fetched G at a time (coalesced, streaming,
+//     L2 evict_first) and broadcast with group-wide shuffles.
+//   * Products are summed in CSR order with separately rounded mul and add
+//     (__fmul_rn / __fadd_rn): bit-identical to scipy's csr_matvecs.
+//   * Power-law hubs: rows longer than the plan's threshold T are cut into
+//     segments of T non-zeros.  Segment blocks are scheduled FIRST in every
+//     panel; each writes a partial row to the workspace and a small finalize
+//     kernel reduces the partials in segment order (deterministic, no atomics)
+//     and applies the epilogue.
+//   * Grid is panel-major: all row blocks of panel 0, then panel 1, ... so the
+//     set of gathered bytes live at any time is n_cols*panel_bytes, which the
+//     caller sizes to stay resident in the 126 MB L2 (evict_last on gathers).
+//   * Epilogue fused: +bias, relu/tanh/sigmoid, highway mix g*Hc + (1-g)*H.
+#include <algorithm>
+#include <vector>
+
+#include "gcg_common.cuh"
+
+struct gcg_plan {
+  int64_t n_rows, n_cols, nnz;
+  const int32_t* indptr;
+  const int32_t* indices;
+  const float* vals;
+  int32_t long_thresh;
+  int64_t n_long, n_seg, max_deg;
+  int32_t* d_seg_row;      // [n_seg]
+  int32_t* d_seg_beg;      // [n_seg]
+  int32_t* d_long_rows;    // [n_long]
+  int32_t* d_long_segptr;  // [n_long+1]
+};
+
+namespace gcg {
+
+struct SpmmArgs {
+  const int* indptr;
+  const int* indices;
+  const float* vals;
+  const float* B;
+  int64_t ldb;
+  float* C;
+  int64_t ldc;
+  int64_t F;
+  int n_rows;
+  int long_thresh;
+  const int* seg_row;
+  const int* seg_beg;
+  int n_seg;
+  const int* long_rows;
+  const int* long_segptr;
+  int n_long;
+  float* part;
+  const float* bias;
+  int act;
+  int accumulate;
+  const float* gate;
+  int64_t ld_gate;
+  const float* carry;
+  int64_t ld_carry;
+  float* conv_out;
+  int64_t ld_conv;
+  int f4_total;
+  int panel_f4;
+  int n_panels;
+  int seg_blocks;
+  int row_blocks;
+};
+
+__device__ __forceinline__ float4 f4_axpy_exact(float4 acc, float v, float4 x) {
+  acc.x = __fadd_rn(acc.x, __fmul_rn(v, x.x));
+  acc.y = __fadd_rn(acc.y, __fmul_rn(v, x.y));
+  acc.z = __fadd_rn(acc.z, __fmul_rn(v, x.z));
+  acc.w = __fadd_rn(acc.w, __fmul_rn(v, x.w));
+  return acc;
+}
+
+__device__ __forceinline__ float gate_mix(float g, float hc, float h) {
+  // g*Hc + (1-g)*H with separately rounded operations (matches the oracle)
+  return __fadd_rn(__fmul_rn(g, hc), __fmul_rn(__fsub_rn(1.f, g), h));
+}
+
+// bias + act + optional highway mix for one float4 of output row `row`
+// at float4 column `c4`; writes C (and conv_out).
+__device__ __forceinline__ void epilogue_store(const SpmmArgs& a, int64_t row, int c4, float4 v,
+                                               uint64_t strm) {
+  float* cp = a.C + row * a.ldc + 4 * (int64_t)c4;
+  if (a.accumulate) {
+    const float4 o = *reinterpret_cast<const float4*>(cp);
+    v.x = __fadd_rn(o.x, v.x); v.y = __fadd_rn(o.y, v.y);
+    v.z = __fadd_rn(o.z, v.z); v.w = __fadd_rn(o.w, v.w);
+  }
+  if (a.bias) {
+    const int64_t c = 4 * (int64_t)c4;
+    v.x = __fadd_rn(v.x, __ldg(a.bias + c));
+    v.y = __fadd_rn(v.y, (c + 1 < a.F) ? __ldg(a.bias + c + 1) : 0.f);
+    v.z = __fadd_rn(v.z, (c + 2 < a.F) ? __ldg(a.bias + c + 2) : 0.f);
+    v.w = __fadd_rn(v.w, (c + 3 < a.F) ? __ldg(a.bias + c + 3) : 0.f);
+  }
+  if (a.act != GCG_ACT_IDENTITY) {
+    v.x = apply_act(v.x, a.act); v.y = apply_act(v.y, a.act);
+    v.z = apply_act(v.z, a.act); v.w = apply_act(v.w, a.act);
+  }
+  if (a.gate) {
+    if (a.conv_out)
+      stg_f4_stream(reinterpret_cast<float4*>(a.conv_out + row * a.ld_conv + 4 * (int64_t)c4), v, strm);
+    const float4 g = ldg_f4_stream(reinterpret_cast<const float4*>(a.gate + row * a.ld_gate + 4 * (int64_t)c4), strm);
+    const float4 h = ldg_f4_stream(reinterpret_cast<const float4*>(a.carry + row * a.ld_carry + 4 * (int64_t)c4), strm);
+    v.x = gate_mix(g.x, v.x, h.x); v.y = gate_mix(g.y, v.y, h.y);
+    v.z = gate_mix(g.z, v.z, h.z); v.w = gate_mix(g.w, v.w, h.w);
+  }
+  stg_f4_stream(reinterpret_cast<float4*>(cp), v, strm);
+}
+
+template <int G, int VPL>
+__global__ void __launch_bounds__(256) spmm_vec_kernel(const SpmmArgs a) {
+  constexpr int RPW = 32 / G;
+  constexpr int RPB = 8 * RPW;
+  constexpr int U = (VPL >= 3) ? 2 : 4;  // gathered rows in flight per group
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int grp = lane / G, s = lane % G;
+  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (grp * G));
+  const int bpp = a.seg_blocks + a.row_blocks;
+  const int panel = blockIdx.x / bpp;
+  const int bip = blockIdx.x - panel * bpp;
+  const uint64_t keep = policy_evict_last(), strm = policy_evict_first();
+
+  int beg, end;
+  int64_t row;
+  bool is_seg;
+  if (bip < a.seg_blocks) {
+    const int seg = bip * RPB + warp * RPW + grp;
+    if (seg >= a.n_seg) return;
+    const int r = __ldg(a.seg_row + seg);
+    beg = __ldg(a.seg_beg + seg);
+    end = min(beg + a.long_thresh, __ldg(a.indptr + r + 1));
+    row = seg;
+    is_seg = true;
+  } else {
+    const int r = (bip - a.seg_blocks) * RPB + warp * RPW + grp;
+    if (r >= a.n_rows) return;
+    beg = __ldg(a.indptr + r);
+    end = __ldg(a.indptr + r + 1);
+    if (end - beg > a.long_thresh) return;  // segment blocks + finalize own this row
+    row = r;
+    is_seg = false;
+  }
+
+  const int c_base = panel * a.panel_f4 + s;
+  bool cv[VPL];
+  float4 acc[VPL];
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) {
+    cv[k] = (c_base + k * G) < a.f4_total;
+    acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const float4* __restrict__ Bp = reinterpret_cast<const float4*>(a.B) + c_base;
+  const int64_t ldb4 = a.ldb >> 2;
+
+  for (int base = beg; base < end; base += G) {
+    const int kk = base + s;
+    int myc = 0;
+    float myv = 0.f;
+    if (kk < end) {
+      myc = ldg_i32_stream(a.indices + kk, strm);
+      myv = ldg_f32_stream(a.vals + kk, strm);
+    }
+    const int cnt = min(G, end - base);
+    int j = 0;
+    for (; j + U <= cnt; j += U) {
+      float4 x[U][VPL];
+      float v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int col = __shfl_sync(gmask, myc, j + u, G);
+        v[u] = __shfl_sync(gmask, myv, j + u, G);
+        const float4* src = Bp + (int64_t)col * ldb4;
+#pragma unroll
+        for (int k = 0; k < VPL; ++k)
+          if (cv[k]) x[u][k] = ldg_f4_keep(src + k * G, keep);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int k = 0; k < VPL; ++k)
+          if (cv[k]) acc[k] = f4_axpy_exact(acc[k], v[u], x[u][k]);
+    }
+    for (; j < cnt; ++j) {
+      const int col = __shfl_sync(gmask, myc, j, G);
+      const float v = __shfl_sync(gmask, myv, j, G);
+      const float4* src = Bp + (int64_t)col * ldb4;
+      float4 x[VPL];
+#pragma unroll
+      for (int k = 0; k < VPL; ++k)
+        if (cv[k]) x[k] = ldg_f4_keep(src + k * G, keep);
+#pragma unroll
+      for (int k = 0; k < VPL; ++k)
+        if (cv[k]) acc[k] = f4_axpy_exact(acc[k], v, x[k]);
+    }
+  }
+
+  if (is_seg) {
+    float4* out = reinterpret_cast<float4*>(a.part + row * a.ldc) + c_base;
+#pragma unroll
+    for (int k = 0; k < VPL; ++k)
+      if (cv[k]) out[k * G] = acc[k];  // re-read soon by finalize: default policy
+  } else {
+#pragma unroll
+    for (int k = 0; k < VPL; ++k)
+      if (cv[k]) epilogue_store(a, row, c_base + k * G, acc[k], strm);
+  }
+}
+
+// One warp per long row: sum the segment partials in order, apply the epilogue.
+__global__ void __launch_bounds__(256) spmm_finalize_kernel(const SpmmArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int li = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (li >= a.n_long) return;
+  const uint64_t strm = policy_evict_first();
+  const int row = __ldg(a.long_rows + li);
+  const int s0 = __ldg(a.long_segptr + li), s1 = __ldg(a.long_segptr + li + 1);
+  for (int c4 = lane; c4 < a.f4_total; c4 += 32) {
+    float4 acc = *(reinterpret_cast<const float4*>(a.part + (int64_t)s0 * a.ldc) + c4);
+    for (int sgi = s0 + 1; sgi < s1; ++sgi) {
+      const float4 p = *(reinterpret_cast<const float4*>(a.part + (int64_t)sgi * a.ldc) + c4);
+      acc.x = __fadd_rn(acc.x, p.x); acc.y = __fadd_rn(acc.y, p.y);
+      acc.z = __fadd_rn(acc.z, p.z); acc.w = __fadd_rn(acc.w, p.w);
+    }
+    epilogue_store(a, row, c4, acc, strm);
+  }
+}
+
+// Scalar fallback: unaligned pointers or leading dimensions that are not
+// multiples of 4.  One warp per row, 32*8 columns per pass, no row splitting.
+__global__ void __launch_bounds__(256) spmm_scalar_kernel(const SpmmArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= a.n_rows) return;
+  const int beg = __ldg(a.indptr + row), end = __ldg(a.indptr + row + 1);
+  for (int64_t c0 = 0; c0 < a.F; c0 += 256) {
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    for (int base = beg; base < end; base += 32) {
+      const int kk = base + lane;
+      const int myc = kk < end ? __ldg(a.indices + kk) : 0;
+      const float myv = kk < end ? __ldg(a.vals + kk) : 0.f;
+      const int cnt = min(32, end - base);
+      for (int j = 0; j < cnt; ++j) {
+        const int col = __shfl_sync(0xffffffffu, myc, j);
+        const float v = __shfl_sync(0xffffffffu, myv, j);
+        const float* src = a.B + (int64_t)col * a.ldb + c0 + lane;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (c0 + lane + 32 * k < a.F) acc[k] = __fadd_rn(acc[k], __fmul_rn(v, __ldg(src + 32 * k)));
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int64_t c = c0 + lane + 32 * k;
+      if (c >= a.F) continue;
+      float v = acc[k];
+      float* cp = a.C + row * a.ldc + c;
+      if (a.accumulate) v = __fadd_rn(*cp, v);
+      if (a.bias) v = __fadd_rn(v, __ldg(a.bias + c));
+      v = apply_act(v, a.act);
+      if (a.gate) {
+        if (a.conv_out) a.conv_out[row * a.ld_conv + c] = v;
+        v = gate_mix(a.gate[row * a.ld_gate + c], v, a.carry[row * a.ld_carry + c]);
+      }
+      *cp = v;
+    }
+  }
+}
+
+template <int G, int VPL>
+static cudaError_t launch_vec(const SpmmArgs& a, cudaStream_t st) {
+  const int64_t grid = (int64_t)a.n_panels * (a.seg_blocks + a.row_blocks);
+  spmm_vec_kernel<G, VPL><<<(unsigned)grid, 256, 0, st>>>(a);
+  return cudaGetLastError();
+}
+
+}  // namespace gcg
+
+using namespace gcg;
+
+extern "C" int gcg_plan_create_csr(int64_t n_rows, int64_t n_cols, int64_t nnz,
+                                   const int32_t* d_indptr, const int32_t* d_indices,
+                                   const float* d_vals, const int32_t* h_indptr,
+                                   int32_t long_row_threshold, gcg_plan** out) {
+  GCG_CHECK_ARG(out != nullptr, "gcg_plan_create_csr: out is NULL");
+  GCG_CHECK_ARG(n_rows >= 0 && n_cols >= 0 && nnz >= 0, "gcg_plan_create_csr: negative size");
+  GCG_CHECK_ARG(n_rows < INT32_MAX && n_cols < INT32_MAX && nnz < INT32_MAX,
+                "gcg_plan_create_csr: int32 CSR indices overflow");
+  GCG_CHECK_ARG(d_indptr && (nnz == 0 || (d_indices && d_vals)), "gcg_plan_create_csr: NULL CSR array");
+  if (long_row_threshold <= 0) long_row_threshold = 256;
+  std::vector<int32_t> hp;
+  if (!h_indptr) {
+    hp.resize(n_rows + 1);
+    GCG_CUDA(cudaMemcpy(hp.data(), d_indptr, sizeof(int32_t) * (n_rows + 1), cudaMemcpyDeviceToHost));
+    h_indptr = hp.data();
+  }
+  // a plan may describe a contiguous row slice of a larger CSR (absolute offsets)
+  GCG_CHECK_SHAPE(h_indptr[0] >= 0 && h_indptr[n_rows] <= nnz,
+                  "gcg_plan_create_csr: indptr[0]=%d indptr[n]=%d but nnz=%lld", h_indptr[0],
+                  h_indptr[n_rows], (long long)nnz);
+  std::vector<int32_t> seg_row, seg_beg, long_rows, long_segptr;
+  int64_t max_deg = 0;
+  const int32_t T = long_row_threshold;
+  for (int64_t r = 0; r < n_rows; ++r) {
+    const int32_t b = h_indptr[r], e = h_indptr[r + 1];
+    GCG_CHECK_SHAPE(e >= b, "gcg_plan_create_csr: indptr not monotone at row %lld", (long long)r);
+    const int32_t deg = e - b;
+    max_deg = std::max<int64_t>(max_deg, deg);
+    if (deg > T) {
+      long_rows.push_back((int32_t)r);
+      long_segptr.push_back((int32_t)seg_row.size());
+      for (int32_t s = b; s < e; s += T) {
+        seg_row.push_back((int32_t)r);
+        seg_beg.push_back(s);
+      }
+    }
+  }
+  long_segptr.push_back((int32_t)seg_row.size());
+  gcg_plan* p = new gcg_plan();
+  p->n_rows = n_rows; p->n_cols = n_cols; p->nnz = nnz;
+  p->indptr = d_indptr; p->indices = d_indices; p->vals = d_vals;
+  p->long_thresh = T;
+  p->n_long = (int64_t)long_rows.size();
+  p->n_seg = (int64_t)seg_row.size();
+  p->max_deg = max_deg;
+  p->d_seg_row = p->d_seg_beg = p->d_long_rows = p->d_long_segptr = nullptr;
+  if (p->n_long > 0) {
+    auto up = [](int32_t** dst, const std::vector<int32_t>& v) -> cudaError_t {
+      cudaError_t e = cudaMalloc(dst, sizeof(int32_t) * v.size());
+      if (e != cudaSuccess) return e;
+      return cudaMemcpy(*dst, v.data(), sizeof(int32_t) * v.size(), cudaMemcpyHostToDevice);
+    };
+    cudaError_t e = up(&p->d_seg_row, seg_row);
+    if (e == cudaSuccess) e = up(&p->d_seg_beg, seg_beg);
+    if (e == cudaSuccess) e = up(&p->d_long_rows, long_rows);
+    if (e == cudaSuccess) e = up(&p->d_long_segptr, long_segptr);
+    if (e != cudaSuccess) {
+      set_error("gcg_plan_create_csr: %s", cudaGetErrorString(e));
+      gcg_plan_destroy(p);
+      return GCG_ERR_CUDA;
+    }
+  }
+  *out = p;
+  return GCG_OK;
+}
+
+extern "C" int gcg_plan_destroy(gcg_plan* p) {
+  if (!p) return GCG_OK;
+  cudaFree(p->d_seg_row);
+  cudaFree(p->d_seg_beg);
+  cudaFree(p->d_long_rows);
+  cudaFree(p->d_long_segptr);
+  delete p;
+  return GCG_OK;
+}
+
+extern "C" int64_t gcg_plan_workspace_bytes(const gcg_plan* p, int64_t ldc) {
+  if (!p || ldc <= 0) return 0;
+  return p->n_seg * ldc * (int64_t)sizeof(float);
+}
+
+extern "C" int gcg_plan_info(const gcg_plan* p, int64_t* info) {
+  GCG_CHECK_ARG(p && info, "gcg_plan_info: NULL argument");
+  info[0] = p->n_rows; info[1] = p->n_cols; info[2] = p->nnz; info[3] = p->n_long;
+  info[4] = p->n_seg; info[5] = p->max_deg; info[6] = p->long_thresh; info[7] = 0;
+  return GCG_OK;
+}
+
+extern "C" int gcg_spmm_csr_f32(const gcg_plan* p, const float* B, int64_t ldb, int64_t F,
+                                float* C, int64_t ldc, const float* bias, int act,
+                                int accumulate, const float* gate, int64_t ld_gate,
+                                const float* carry, int64_t ld_carry, float* conv_out,
+                                int64_t ld_conv, int32_t panel_cols, void* workspace,
+                                int64_t workspace_bytes, void* stream) {
+  GCG_CHECK_ARG(p != nullptr, "gcg_spmm_csr_f32: plan is NULL");
+  GCG_CHECK_ARG(B && C, "gcg_spmm_csr_f32: NULL dense operand");
+  GCG_CHECK_ARG(B != C, "gcg_spmm_csr_f32: B and C must not alias");
+  GCG_CHECK_SHAPE(F > 0 && ldb >= F && ldc >= F, "gcg_spmm_csr_f32: F=%lld ldb=%lld ldc=%lld",
+                  (long long)F, (long long)ldb, (long long)ldc);
+  GCG_CHECK_ARG(act >= GCG_ACT_IDENTITY && act <= GCG_ACT_SIGMOID, "gcg_spmm_csr_f32: bad act %d", act);
+  GCG_CHECK_ARG((gate == nullptr) == (carry == nullptr), "gcg_spmm_csr_f32: gate and carry go together");
+  if (gate) {
+    GCG_CHECK_SHAPE(ld_gate >= F && ld_carry >= F && (!conv_out || ld_conv >= F),
+                    "gcg_spmm_csr_f32: gate/carry/conv leading dimensions smaller than F");
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (p->n_rows == 0) return GCG_OK;
+
+  SpmmArgs a;
+  a.indptr = p->indptr; a.indices = p->indices; a.vals = p->vals;
+  a.B = B; a.ldb = ldb; a.C = C; a.ldc = ldc; a.F = F;
+  a.n_rows = (int)p->n_rows; a.long_thresh = p->long_thresh;
+  a.seg_row = p->d_seg_row; a.seg_beg = p->d_seg_beg; a.n_seg = (int)p->n_seg;
+  a.long_rows = p->d_long_rows; a.long_segptr = p->d_long_segptr; a.n_long = (int)p->n_long;
+  a.part = reinterpret_cast<float*>(workspace);
+  a.bias = bias; a.act = act; a.accumulate = accumulate;
+  a.gate = gate; a.ld_gate = ld_gate; a.carry = carry; a.ld_carry = ld_carry;
+  a.conv_out = conv_out; a.ld_conv = ld_conv;
+  a.f4_total = (int)((F + 3) / 4);
+
+  const int64_t f_pad = 4 * (int64_t)a.f4_total;
+  bool vec = aligned16(B) && aligned16(C) && (ldb % 4 == 0) && (ldc % 4 == 0) && ldb >= f_pad && ldc >= f_pad;
+  if (gate)
+    vec = vec && aligned16(gate) && aligned16(carry) && (ld_gate % 4 == 0) && (ld_carry % 4 == 0) &&
+          ld_gate >= f_pad && ld_carry >= f_pad &&
+          (!conv_out || (aligned16(conv_out) && ld_conv % 4 == 0 && ld_conv >= f_pad));
+  if (!vec) {
+    a.n_seg = 0; a.n_long = 0; a.long_thresh = INT32_MAX;
+    a.panel_f4 = a.f4_total; a.n_panels = 1; a.seg_blocks = 0; a.row_blocks = 0;
+    spmm_scalar_kernel<<<(unsigned)ceil_div(p->n_rows, 8), 256, 0, st>>>(a);
+    GCG_LAUNCH_CHECK();
+    return GCG_OK;
+  }
+  if (p->n_seg > 0) {
+    GCG_CHECK_ARG(workspace != nullptr && workspace_bytes >= gcg_plan_workspace_bytes(p, ldc),
+                  "gcg_spmm_csr_f32: workspace too small (%lld < %lld)", (long long)workspace_bytes,
+                  (long long)gcg_plan_workspace_bytes(p, ldc));
+    GCG_CHECK_ARG(aligned16(workspace), "gcg_spmm_csr_f32: workspace must be 16-byte aligned");
+  }
+
+  // choose (G, VPL): panel width in float4 = G*VPL
+  int want_f4 = a.f4_total;
+  if (panel_cols > 0) want_f4 = (int)std::min<int64_t>(a.f4_total, std::max<int64_t>(1, (panel_cols + 3) / 4));
+  int G, VPL;
+  if (want_f4 <= 4) { G = 4; VPL = 1; }
+  else if (want_f4 <= 8) { G = 8; VPL = 1; }
+  else if (want_f4 <= 16) { G = 16; VPL = 1; }
+  else { G = 32; VPL = (int)std::min<int64_t>(5, ceil_div(want_f4, 32)); }
+  a.panel_f4 = G * VPL;
+  a.n_panels = (int)ceil_div(a.f4_total, a.panel_f4);
+  const int rpb = 8 * (32 / G);
+  a.seg_blocks = (int)ceil_div(p->n_seg, rpb);
+  a.row_blocks = (int)ceil_div(p->n_rows, rpb);
+  GCG_CHECK_SHAPE((int64_t)a.n_panels * (a.seg_blocks + a.row_blocks) < INT32_MAX, "gcg_spmm_csr_f32: grid too large");
+
+  cudaError_t e;
+  switch (G * 8 + VPL) {
+    case 4 * 8 + 1: e = launch_vec<4, 1>(a, st); break;
+    case 8 * 8 + 1: e = launch_vec<8, 1>(a, st); break;
+    case 16 * 8 + 1: e = launch_vec<16, 1>(a, st); break;
+    case 32 * 8 + 1: e = launch_vec<32, 1>(a, st); break;
+    case 32 * 8 + 2: e = launch_vec<32, 2>(a, st); break;
+    case 32 * 8 + 3: e = launch_vec<32, 3>(a, st); break;
+    case 32 * 8 + 4: e = launch_vec<32, 4>(a, st); break;
+    default: e = launch_vec<32, 5>(a, st); break;
+  }
+  if (e != cudaSuccess) {
+    set_error("gcg_spmm_csr_f32: launch failed: %s", cudaGetErrorString(e));
+    return GCG_ERR_CUDA;
+  }
+  count_launch();
+  if (p->n_long > 0) {
+    spmm_finalize_kernel<<<(unsigned)ceil_div(p->n_long, 8), 256, 0, st>>>(a);
+    GCG_LAUNCH_CHECK();
+  }
+  return GCG_OK;
+}

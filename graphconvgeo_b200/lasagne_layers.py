@@ -1,0 +1,476 @@
+"""The reference's layer API for the GCN propagation path, on B200.
+
+Mirrors /root/reference/lasagne_layers.py:20-89 (byte-identical copies live in
+mlpconv.py:27-95 and mlp.py:36-45): same class names, same constructor keywords
+(``incoming, num_units, W=, b=, nonlinearity=, H=``) and the same
+``get_output_for(input, **kwargs)`` entry point honouring ``target_indices``
+(:81) and ``deterministic`` (:32,37).  The bodies call the hand-written sm_100a
+kernels of libgcg.so instead of Theano's S.dot / T.dot; there is no Theano
+graph, so ``get_output_for`` executes eagerly on CUDA tensors.
+
+Because there is no symbolic autodiff either, every layer also implements
+``backward(grad_output)`` (the products theano.grad derives at mlpconv.py:263),
+storing parameter gradients in ``layer.grads``.
+
+Extension (BASELINE.json north_star, not in the reference):
+``HighwayConvolutionDenseLayer`` -- a conv layer whose output is gated with its
+input, out = g*H' + (1-g)*H, g = sigmoid(H.W_g + b_g); the mix is fused into the
+SpMM epilogue.  ``GraphConvLayer`` is the north_star's name for the conv layers.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import ops
+from .sparse import CSRMatrix, as_csr, is_sparse
+
+# --------------------------------------------------------------------------- #
+# lasagne.nonlinearities / lasagne.init look-alikes                            #
+# --------------------------------------------------------------------------- #
+
+
+class _NL(str):
+    """A non-linearity name that can also be compared / passed like Lasagne's functions."""
+
+
+class nonlinearities:
+    rectify = _NL("rectify")
+    tanh = _NL("tanh")
+    sigmoid = _NL("sigmoid")
+    softmax = _NL("softmax")
+    identity = linear = _NL("identity")
+
+
+def _nl_name(nl):
+    if nl is None:
+        return "identity"
+    if isinstance(nl, str):
+        name = str(nl)
+    else:
+        name = getattr(nl, "__name__", None)
+    if name == "relu":
+        name = "rectify"
+    if name == "linear":
+        name = "identity"
+    if name not in ("rectify", "tanh", "sigmoid", "softmax", "identity"):
+        raise ValueError("unsupported nonlinearity %r" % (nl,))
+    return name
+
+
+class GlorotUniform:
+    """lasagne.init.GlorotUniform (mlpconv.py:208): U(-a, a), a = sqrt(6/(fan_in+fan_out))."""
+
+    def __init__(self, gain=1.0):
+        self.gain = gain
+
+    def sample(self, shape, rng=None):
+        rng = np.random if rng is None else rng
+        a = self.gain * np.sqrt(6.0 / (shape[0] + shape[1]))
+        return rng.uniform(-a, a, size=shape).astype(np.float32)
+
+
+class Constant:
+    def __init__(self, val=0.0):
+        self.val = val
+
+    def sample(self, shape, rng=None):
+        return np.full(shape, self.val, dtype=np.float32)
+
+
+class init:
+    GlorotUniform = GlorotUniform
+    Constant = Constant
+
+
+def _to_param(spec, shape, device, rng=None):
+    if spec is None:
+        return None
+    if hasattr(spec, "sample"):
+        arr = spec.sample(shape, rng)
+    elif isinstance(spec, torch.Tensor):
+        t = spec.to(device=device, dtype=torch.float32).contiguous()
+        assert tuple(t.shape) == tuple(shape), "parameter shape %s != %s" % (tuple(t.shape), shape)
+        return t
+    else:
+        arr = np.asarray(spec, dtype=np.float32)
+    assert tuple(arr.shape) == tuple(shape), "parameter shape %s != %s" % (arr.shape, shape)
+    return torch.from_numpy(np.ascontiguousarray(arr)).to(device)
+
+
+# --------------------------------------------------------------------------- #
+# Layer protocol                                                               #
+# --------------------------------------------------------------------------- #
+
+
+class Layer:
+    def __init__(self, incoming, name=None, device="cuda"):
+        if isinstance(incoming, Layer):
+            self.input_layer = incoming
+            self.input_shape = incoming.output_shape
+            self.device = incoming.device
+        else:
+            self.input_layer = None
+            self.input_shape = tuple(incoming)
+            self.device = torch.device(device)
+        self.name = name
+        self.params = []          # [(name, tensor, tags)]
+        self.grads = {}
+        self._buf = {}
+
+    @property
+    def output_shape(self):
+        return self.get_output_shape_for(self.input_shape)
+
+    def get_output_shape_for(self, input_shape):
+        return input_shape
+
+    def get_params(self, **tags):
+        out = []
+        for _, t, ptags in self.params:
+            if all(ptags.get(k, False) == v for k, v in tags.items()):
+                out.append(t)
+        return out
+
+    def get_output_for(self, input, **kwargs):
+        raise NotImplementedError
+
+    def backward(self, grad_output, **kwargs):
+        raise NotImplementedError
+
+    # persistent, shape-keyed buffers: nothing is allocated in the steady state,
+    # which keeps the epoch CUDA-graph capturable
+    def _mat(self, key, n_rows, n_cols, zero=False):
+        b = self._buf.get(key)
+        if b is None or b.shape != (n_rows, n_cols):
+            b = ops.alloc_mat(n_rows, n_cols, self.device, zero=zero)
+            self._buf[key] = b
+        return b
+
+    def _vecbuf(self, key, n, dtype=torch.float32):
+        b = self._buf.get(key)
+        if b is None or b.numel() != n or b.dtype != dtype:
+            b = torch.empty(n, dtype=dtype, device=self.device)
+            self._buf[key] = b
+        return b
+
+
+class InputLayer(Layer):
+    """lasagne.layers.InputLayer (mlpconv.py:196-197)."""
+
+    def __init__(self, shape, input_var=None, name=None, device="cuda"):
+        super().__init__(shape, name=name, device=device)
+        self.shape = tuple(shape)
+        self.input_var = input_var
+
+    def get_output_for(self, input, **kwargs):
+        return input
+
+
+class DenseLayer(Layer):
+    """lasagne.layers.DenseLayer: W [num_inputs, num_units] (regularizable, trainable),
+    b [num_units] (trainable); act(input.W + b)."""
+
+    def __init__(self, incoming, num_units, W=None, b=Constant(0.0), nonlinearity=nonlinearities.rectify,
+                 name=None, rng=None, **kwargs):
+        super().__init__(incoming, name=name, **kwargs)
+        self.num_units = int(num_units)
+        self.nonlinearity = _nl_name(nonlinearity)
+        num_inputs = int(np.prod(self.input_shape[1:]))
+        self.num_inputs = num_inputs
+        W = GlorotUniform() if W is None else W
+        self.W = _to_param(W, (num_inputs, self.num_units), self.device, rng)
+        self.b = _to_param(b, (self.num_units,), self.device, rng)
+        self.params.append(("W", self.W, dict(trainable=True, regularizable=True)))
+        if self.b is not None:
+            self.params.append(("b", self.b, dict(trainable=True, regularizable=False)))
+
+    def get_output_shape_for(self, input_shape):
+        return (input_shape[0], self.num_units)
+
+    def get_output_for(self, input, **kwargs):
+        if self.nonlinearity == "softmax":
+            raise NotImplementedError("dense softmax head is outside the GCN hot path")
+        return ops.gemm(input, self.W, bias=self.b, act=self.nonlinearity,
+                        out=self._mat("out", input.shape[0], self.num_units))
+
+    def _grad(self, key, like):
+        g = self.grads.get(key)
+        if g is None:
+            g = torch.zeros_like(like)
+            self.grads[key] = g
+        return g
+
+
+def _check_sparse(input):
+    # lasagne_layers.py:22-24, 33-35, 61-63
+    if not is_sparse(input):
+        raise ValueError("Input for this layer must be sparse")
+
+
+class SparseInputDenseLayer(DenseLayer):
+    """act(X.W + b) for CSR X -- lasagne_layers.py:20-29."""
+
+    def get_output_for(self, input, **kwargs):
+        _check_sparse(input)
+        X = as_csr(input, self.device)
+        self._X = X
+        out = ops.spmm(X, self.W, bias=self.b, act=self.nonlinearity,
+                       out=self._mat("out", X.shape[0], self.num_units))     # :26-29
+        self._out = out
+        return out
+
+    def backward(self, grad_output, preact=False, **kwargs):
+        """grad wrt the activation output (or the pre-activation when ``preact``).
+        dW = X^T.dP (Dot.grad), db = colsum(dP).  X is an input: no grad is returned."""
+        dP = grad_output if preact or self.nonlinearity == "identity" else \
+            ops.act_bwd(grad_output, self._out, self.nonlinearity, out=self._mat("dP", *grad_output.shape))
+        if self.b is not None:
+            ops.colsum(dP, out=self._grad("b", self.b))
+        ops.spmm(self._X.T, dP, out=self._grad("W", self.W))
+        return None
+
+
+class SparseInputDropoutLayer(Layer):
+    """Dropout on a sparse input -- lasagne_layers.py:31-52.  ``deterministic=True`` or
+    p == 0 returns the input unchanged (:37-38).  The stochastic branch draws its mask
+    from torch's CUDA generator; it cannot reproduce Theano's MRG stream, so parity
+    configurations run with dropout off (as the reference driver does, tensormain.py:234)."""
+
+    def __init__(self, incoming, p=0.5, rescale=True, **kwargs):
+        super().__init__(incoming, **kwargs)
+        self.p = float(p)
+        self.rescale = rescale
+
+    def get_output_for(self, input, deterministic=False, **kwargs):
+        _check_sparse(input)
+        if deterministic or self.p == 0:
+            return input
+        X = as_csr(input, self.device)
+        retain = 1.0 - self.p
+        keep = (torch.rand(X.data.shape, device=X.data.device) < retain).to(torch.float32)
+        data = X.data * keep * ((1.0 / retain) if self.rescale else 1.0)      # :44-52
+        return CSRMatrix(X.indptr, X.indices, data, X.shape, long_row_threshold=X.long_row_threshold)
+
+
+class TargetIndices:
+    """A ``target_indices`` vector (mlpconv.py:179, tensormain.py:225-230) prepared once:
+    device copy, the row-gathered A_hat[idx, :] (so only wanted rows are ever propagated)
+    and the inverse map used by the deterministic scatter-add of the backward."""
+
+    def __init__(self, idx, H: CSRMatrix):
+        self.host = np.ascontiguousarray(np.asarray(idx), dtype=np.int32)
+        self.n = len(self.host)
+        self.device = H.device
+        self.dev = torch.from_numpy(self.host).to(self.device)
+        self.H = H
+        self._Hsub = None
+        self._pos = None
+
+    @property
+    def Hsub(self):
+        if self._Hsub is None:
+            self._Hsub = self.H.gather_rows(self.host)
+        return self._Hsub
+
+    @property
+    def positions(self):
+        if self._pos is None:
+            self._pos = ops.scatter_positions(self.host, self.H.shape[0], self.device)
+        return self._pos
+
+
+class _ConvBase(DenseLayer):
+    def __init__(self, incoming, H=None, **kwargs):
+        super().__init__(incoming, **kwargs)
+        self.H = None if H is None else as_csr(H, self.device)    # lasagne_layers.py:56,77 (not a param)
+        self._ti_cache = {}
+
+    def _target(self, target_indices):
+        if target_indices is None or isinstance(target_indices, TargetIndices):
+            return target_indices
+        key = (id(target_indices), len(target_indices))
+        hit = self._ti_cache.get(key)
+        if hit is None:
+            hit = (target_indices, TargetIndices(target_indices, self.H))   # keep the array alive: id is the key
+            self._ti_cache[key] = hit
+        return hit[1]
+
+
+class SparseConvolutionDenseLayer(_ConvBase):
+    """act(H.(X.W) + b) for CSR X -- lasagne_layers.py:53-71 (GCN layer 1, mlpconv.py:205-209)."""
+
+    def get_output_for(self, input, **kwargs):
+        _check_sparse(input)                                               # :61-63
+        X = as_csr(input, self.device)
+        self._X = X
+        N = X.shape[0]
+        z = ops.spmm(X, self.W, out=self._mat("Z", N, self.num_units))      # :65
+        out = ops.spmm(self.H, z, bias=self.b, act=self.nonlinearity,
+                       out=self._mat("out", N, self.num_units))             # :67-71 (bias+act fused)
+        self._out = out
+        return out
+
+    def backward(self, grad_output, preact=False, **kwargs):
+        dP = grad_output if preact or self.nonlinearity == "identity" else \
+            ops.act_bwd(grad_output, self._out, self.nonlinearity, out=self._mat("dP", *grad_output.shape))
+        if self.b is not None:
+            ops.colsum(dP, out=self._grad("b", self.b))
+        dZ = ops.spmm(self.H, dP, out=self._mat("Z", *dP.shape))            # A_hat^T = A_hat; Z is dead: reuse
+        ops.spmm(self._X.T, dZ, out=self._grad("W", self.W))                # dW = X^T.dZ
+        return None
+
+
+class ConvolutionDenseLayer(_ConvBase):
+    """act((H.(input.W) + b)[target_indices, :]) -- lasagne_layers.py:73-89.
+
+    ``nonlinearity=softmax`` is the output layer of mlpconv.py:213-216.  Only the rows in
+    ``target_indices`` are propagated (A_hat[idx,:].Z), which equals gathering afterwards.
+    kwargs: ``target_indices`` (array or TargetIndices; None keeps every row),
+    ``logits=True`` returns the pre-softmax rows (the training step feeds them to the
+    fused softmax/CE head)."""
+
+    def get_output_for(self, input, **kwargs):
+        ti = self._target(kwargs.get("target_indices"))                    # :81
+        N = input.shape[0]
+        self._in = input
+        self._ti = ti
+        z = ops.gemm(input, self.W, out=self._mat("Z", N, self.num_units))   # :82
+        Hm = self.H if ti is None else ti.Hsub
+        n_out = N if ti is None else ti.n
+        fused_act = "identity" if self.nonlinearity == "softmax" else self.nonlinearity
+        out = ops.spmm(Hm, z, bias=self.b, act=fused_act,
+                       out=self._mat(("out", n_out), n_out, self.num_units))  # :84-88
+        self._out = out
+        if self.nonlinearity == "softmax" and not kwargs.get("logits", False):
+            probs = self._mat(("probs", n_out), n_out, self.num_units)
+            ops.softmax_ce(out, probs=probs)                               # :89
+            return probs
+        return out
+
+    def backward(self, grad_output, preact=False, input_mask=None, need_input_grad=True, **kwargs):
+        """``grad_output``: grad wrt the layer output rows (wrt the LOGITS for a softmax
+        layer -- the head produces it fused with the loss).  ``input_mask=(A_prev, act)``
+        fuses the previous layer's act' into the dH product."""
+        ti = self._ti
+        N = self._in.shape[0]
+        if self.nonlinearity in ("softmax", "identity") or preact:
+            dPr = grad_output
+        else:
+            dPr = ops.act_bwd(grad_output, self._out, self.nonlinearity,
+                              out=self._mat("dPr", *grad_output.shape))
+        if ti is not None:
+            ptr, pos = ti.positions
+            dP = ops.scatter_rows(dPr, ptr, pos, N, out=self._mat("dP", N, self.num_units))  # grad of :88
+        else:
+            dP = dPr
+        if self.b is not None:
+            ops.colsum(dP, out=self._grad("b", self.b))
+        dZ = ops.spmm(self.H, dP, out=self._mat("Z", N, self.num_units))     # A_hat^T.dP
+        ops.gemm(self._in, dZ, transA=True, out=self._grad("W", self.W))     # dW = H_in^T.dZ
+        if not need_input_grad:
+            return None
+        mk, mact = (None, "identity") if input_mask is None else input_mask
+        return ops.gemm(dZ, self.W, transB=True, mask=mk, mask_act=mact,
+                        out=self._mat("dIn", N, self.num_inputs))            # dH = dZ.W^T
+
+
+class HighwayConvolutionDenseLayer(ConvolutionDenseLayer):
+    """Gated conv layer (north_star; not in the reference):
+        H' = act(A_hat.(H.W) + b);  g = sigmoid(H.W_g + b_g);  out = g*H' + (1-g)*H
+    in-dim must equal out-dim.  The bias/act/mix epilogue is fused into the SpMM, so H'
+    only reaches HBM in training mode (``train=True``), where the backward needs it."""
+
+    def __init__(self, incoming, H=None, Wg=None, bg=Constant(0.0), rng=None, **kwargs):
+        super().__init__(incoming, H=H, rng=rng, **kwargs)
+        assert self.num_inputs == self.num_units, "highway gate needs in-dim == out-dim"
+        assert self.nonlinearity != "softmax"
+        Wg = GlorotUniform() if Wg is None else Wg
+        self.Wg = _to_param(Wg, (self.num_inputs, self.num_units), self.device, rng)
+        self.bg = _to_param(bg, (self.num_units,), self.device, rng)
+        self.params.append(("Wg", self.Wg, dict(trainable=True, regularizable=True)))
+        self.params.append(("bg", self.bg, dict(trainable=True, regularizable=False)))
+
+    def get_output_for(self, input, **kwargs):
+        assert kwargs.get("target_indices") is None, "a gated layer keeps all rows"
+        N, h = input.shape[0], self.num_units
+        self._in = input
+        z = ops.gemm(input, self.W, out=self._mat("Z", N, h))
+        g = ops.gemm(input, self.Wg, bias=self.bg, act="sigmoid", out=self._mat("g", N, h))
+        conv = self._mat("Hc", N, h) if kwargs.get("train", False) else None
+        out = ops.spmm(self.H, z, bias=self.b, act=self.nonlinearity, gate=g, carry=input, conv_out=conv,
+                       out=self._mat("out", N, h))
+        self._g, self._Hc, self._out = g, conv, out
+        return out
+
+    def backward(self, grad_output, input_mask=None, **kwargs):
+        assert self._Hc is not None, "forward must run with train=True before backward"
+        N, h = grad_output.shape
+        dP, dG, dIn = ops.highway_bwd(grad_output, self._g, self._Hc, self._in, self.nonlinearity,
+                                      dP=self._mat("dP", N, h), dGpre=self._mat("dG", N, h),
+                                      dHin=self._mat("dIn", N, h))
+        ops.colsum(dP, out=self._grad("b", self.b))
+        ops.colsum(dG, out=self._grad("bg", self.bg))
+        dZ = ops.spmm(self.H, dP, out=self._mat("Z", N, h))
+        ops.gemm(self._in, dZ, transA=True, out=self._grad("W", self.W))
+        ops.gemm(self._in, dG, transA=True, out=self._grad("Wg", self.Wg))
+        ops.gemm(dZ, self.W, transB=True, beta=1.0, out=dIn)
+        mk, mact = (None, "identity") if input_mask is None else input_mask
+        ops.gemm(dG, self.Wg, transB=True, beta=1.0, mask=mk, mask_act=mact, out=dIn)
+        return dIn
+
+
+def GraphConvLayer(incoming, H=None, sparse_input=False, highway=False, **kwargs):
+    """north_star's name for the graph-conv layer: picks the reference class."""
+    if sparse_input:
+        return SparseConvolutionDenseLayer(incoming, H=H, **kwargs)
+    if highway:
+        return HighwayConvolutionDenseLayer(incoming, H=H, **kwargs)
+    return ConvolutionDenseLayer(incoming, H=H, **kwargs)
+
+
+# --------------------------------------------------------------------------- #
+# lasagne.layers helper functions used by MLPCONV (mlpconv.py:222,226,262,301,312)
+# --------------------------------------------------------------------------- #
+
+
+def get_all_layers(layer):
+    chain = []
+    while layer is not None:
+        chain.append(layer)
+        layer = layer.input_layer
+    return chain[::-1]
+
+
+def get_output(layer, inputs=None, **kwargs):
+    """lasagne.layers.get_output: run the chain; every layer sees the same kwargs."""
+    x = inputs
+    for ly in get_all_layers(layer):
+        if isinstance(ly, InputLayer):
+            x = ly.input_var if x is None else x
+            continue
+        x = ly.get_output_for(x, **kwargs)
+    return x
+
+
+def get_all_params(layer, **tags):
+    out = []
+    for ly in get_all_layers(layer):
+        out += ly.get_params(**tags)
+    return out
+
+
+def get_all_param_values(layer):
+    return [p.detach().cpu().numpy().copy() for p in get_all_params(layer)]
+
+
+def set_all_param_values(layer, values):
+    params = get_all_params(layer)
+    if len(params) != len(values):
+        raise ValueError("mismatch: got %d values to set %d parameters" % (len(values), len(params)))
+    for p, v in zip(params, values):
+        v = np.asarray(v, dtype=np.float32)
+        if tuple(v.shape) != tuple(p.shape):
+            raise ValueError("mismatch: parameter has shape %r but value to set has shape %r"
+                             % (tuple(p.shape), v.shape))
+        p.copy_(torch.from_numpy(np.ascontiguousarray(v)))

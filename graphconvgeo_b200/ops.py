@@ -1,0 +1,351 @@
+"""Thin Python wrappers over the libgcg.so C ABI (include/gcg.h).
+
+torch is used only for device memory and the current CUDA stream.  Every
+function raises if its inputs are not CUDA float32 tensors -- there is no CPU
+or PyTorch fallback for the hot ops.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+import torch
+
+from . import _lib
+from .sparse import CSRMatrix
+
+# L2 budget used to pick the SpMM column-panel width: one panel of the gathered
+# operand (n_cols * panel * 4 bytes) should stay resident in the 126 MB L2.
+L2_PANEL_BUDGET_BYTES = int(os.environ.get("GCG_L2_PANEL_BUDGET", 64 << 20))
+_FORCE_PANEL = os.environ.get("GCG_SPMM_PANEL")          # experiments: force panel_cols
+_GEMM_MODE = os.environ.get("GCG_GEMM_MODE", "auto")     # "fma" | "tf32x3" | "tf32" | "auto"
+
+_tc_available = None
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+def alloc_mat(n_rows, n_cols, device, zero=False):
+    """[n_rows, n_cols] float32 view whose leading dimension is a multiple of 4
+    floats (16-byte aligned rows) so that every kernel takes its 128-bit path."""
+    ld = round_up(max(int(n_cols), 1), 4)
+    buf = (torch.zeros if zero else torch.empty)((int(n_rows), ld), dtype=torch.float32, device=device)
+    return buf[:, :n_cols] if ld != n_cols else buf
+
+
+def _mat(t, name="tensor"):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise TypeError("%s must be a CUDA tensor (no CPU fallback)" % name)
+    if t.dtype != torch.float32 or t.dim() != 2:
+        raise TypeError("%s must be a 2-D float32 tensor" % name)
+    if t.shape[1] > 1 and t.stride(1) != 1:
+        raise ValueError("%s must be row-major (unit column stride)" % name)
+    ld = t.stride(0) if t.shape[0] > 1 else max(t.stride(0), t.shape[1])
+    return C.c_void_p(t.data_ptr()), int(ld)
+
+
+def _vec(t, name="tensor", dtype=torch.float32):
+    if t is None:
+        return None
+    if not t.is_cuda or t.dtype != dtype or not t.is_contiguous():
+        raise TypeError("%s must be a contiguous CUDA %s tensor" % (name, dtype))
+    return C.c_void_p(t.data_ptr())
+
+
+# ------------------------------------------------------------------ scratch
+class _Scratch:
+    """One growing scratch buffer per (device, stream): all libgcg calls on a
+    stream are ordered, so consecutive ops can share it."""
+
+    def __init__(self):
+        self.bufs = {}
+
+    def get(self, nbytes, device):
+        if nbytes <= 0:
+            return None, 0
+        key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+        buf = self.bufs.get(key)
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty(round_up(int(nbytes * 1.25), 512), dtype=torch.uint8, device=device)
+            self.bufs[key] = buf
+        return C.c_void_p(buf.data_ptr()), buf.numel()
+
+    def reserve(self, nbytes, device):
+        self.get(nbytes, device)
+
+
+scratch = _Scratch()
+
+
+# --------------------------------------------------------------------- SpMM
+def auto_panel_cols(n_cols, F):
+    if _FORCE_PANEL is not None:
+        return int(_FORCE_PANEL)
+    if n_cols * F * 4 <= L2_PANEL_BUDGET_BYTES:
+        return 0
+    p = 16
+    while p * 2 < F and n_cols * (p * 2) * 4 <= L2_PANEL_BUDGET_BYTES:
+        p *= 2
+    return p
+
+
+def spmm(A: CSRMatrix, B, out=None, bias=None, act="identity", accumulate=False, gate=None, carry=None,
+         conv_out=None, panel_cols=None):
+    """out = epilogue(A @ B) -- gcg_spmm_csr_f32 (S.dot, lasagne_layers.py:26,65,67,84)."""
+    L = _lib.lib()
+    bp, ldb = _mat(B, "B")
+    n, k = A.shape
+    F = B.shape[1]
+    if B.shape[0] != k:
+        raise ValueError("spmm: A is %s but B has %d rows" % (A.shape, B.shape[0]))
+    if out is None:
+        out = alloc_mat(n, F, B.device)
+    if out.shape != (n, F):
+        raise ValueError("spmm: out has shape %s, expected %s" % (tuple(out.shape), (n, F)))
+    cp, ldc = _mat(out, "out")
+    gp = hp = vp = None
+    ldg = ldh = ldv = 0
+    if gate is not None:
+        gp, ldg = _mat(gate, "gate")
+        hp, ldh = _mat(carry, "carry")
+        if conv_out is not None:
+            vp, ldv = _mat(conv_out, "conv_out")
+    if panel_cols is None:
+        panel_cols = auto_panel_cols(k, F)
+    ws, wsb = scratch.get(A.workspace_bytes(ldc), B.device)
+    _lib.check(L.gcg_spmm_csr_f32(A.plan, bp, ldb, F, cp, ldc, _vec(bias, "bias"), _lib.act_code(act),
+                                  int(bool(accumulate)), gp, ldg, hp, ldh, vp, ldv, int(panel_cols), ws, wsb,
+                                  _stream()), "gcg_spmm_csr_f32")
+    return out
+
+
+# --------------------------------------------------------------------- GEMM
+def gemm_mode_for(M, N, K):
+    """Engine choice for a dense projection: tcgen05 3xTF32 when the contraction is
+    large enough to be compute-bound on FFMA, else fused FMA tiles."""
+    global _tc_available
+    if _GEMM_MODE != "auto":
+        return _lib.GEMM_MODE[_GEMM_MODE]
+    if _tc_available is None:
+        _tc_available = hasattr(_lib.lib(), "gcg_gemm_tc_available") and bool(_lib.lib().gcg_gemm_tc_available())
+    if _tc_available and 2.0 * M * N * K >= 2e9:
+        return _lib.GEMM_MODE["tf32x3"]
+    return _lib.GEMM_MODE["fma"]
+
+
+def gemm(A, B, out=None, transA=False, transB=False, beta=0.0, bias=None, act="identity", mask=None,
+         mask_act="identity", mode=None, split_k=0):
+    """out = act(op(A) @ op(B) + beta*out + bias) [* act'(mask)] -- gcg_gemm_f32 (T.dot, lasagne_layers.py:82)."""
+    L = _lib.lib()
+    ap, lda = _mat(A, "A")
+    bp, ldb = _mat(B, "B")
+    M, K = (A.shape[1], A.shape[0]) if transA else A.shape
+    K2, N = (B.shape[1], B.shape[0]) if transB else B.shape
+    if K != K2:
+        raise ValueError("gemm: inner dimensions differ (%d vs %d)" % (K, K2))
+    if out is None:
+        if beta != 0.0:
+            raise ValueError("gemm: beta != 0 needs an existing out")
+        out = alloc_mat(M, N, A.device)
+    if out.shape != (M, N):
+        raise ValueError("gemm: out has shape %s, expected %s" % (tuple(out.shape), (M, N)))
+    cp, ldc = _mat(out, "out")
+    mp, ldm = (None, 0) if mask is None else _mat(mask, "mask")
+    if mode is None:
+        mode = gemm_mode_for(M, N, K)
+    elif isinstance(mode, str):
+        mode = _lib.GEMM_MODE[mode]
+    wbytes = L.gcg_gemm_workspace_bytes(int(transA), int(transB), M, N, K, mode, int(split_k))
+    ws, wsb = scratch.get(wbytes, A.device)
+    _lib.check(L.gcg_gemm_f32(int(transA), int(transB), M, N, K, ap, lda, bp, ldb, cp, ldc, float(beta),
+                              _vec(bias, "bias"), _lib.act_code(act), mp, ldm, _lib.act_code(mask_act), mode,
+                              int(split_k), ws, wsb, _stream()), "gcg_gemm_f32")
+    return out
+
+
+# ------------------------------------------------- epilogues / reductions
+def colsum(X, out=None):
+    L = _lib.lib()
+    xp, ld = _mat(X, "X")
+    n, F = X.shape
+    if out is None:
+        out = torch.empty(F, dtype=torch.float32, device=X.device)
+    ws, wsb = scratch.get(L.gcg_colsum_workspace_bytes(n, F), X.device)
+    _lib.check(L.gcg_colsum_f32(xp, ld, n, F, _vec(out, "out"), ws, wsb, _stream()), "gcg_colsum_f32")
+    return out
+
+
+def act_bwd(dA, A, act, out=None):
+    L = _lib.lib()
+    dp, ldd = _mat(dA, "dA")
+    ap, lda = _mat(A, "A")
+    if out is None:
+        out = alloc_mat(dA.shape[0], dA.shape[1], dA.device)
+    op, ldo = _mat(out, "out")
+    _lib.check(L.gcg_act_bwd_f32(dp, ldd, ap, lda, op, ldo, dA.shape[0], dA.shape[1], _lib.act_code(act),
+                                 _stream()), "gcg_act_bwd_f32")
+    return out
+
+
+def highway_bwd(dO, g, Hc, Hin, act, dP=None, dGpre=None, dHin=None):
+    L = _lib.lib()
+    n, F = dO.shape
+    dev = dO.device
+    dP = alloc_mat(n, F, dev) if dP is None else dP
+    dGpre = alloc_mat(n, F, dev) if dGpre is None else dGpre
+    dHin = alloc_mat(n, F, dev) if dHin is None else dHin
+    a = [_mat(t, nm) for t, nm in ((dO, "dO"), (g, "g"), (Hc, "Hc"), (Hin, "Hin"), (dP, "dP"),
+                                   (dGpre, "dGpre"), (dHin, "dHin"))]
+    flat = [x for pair in a for x in pair]
+    _lib.check(L.gcg_highway_bwd_f32(*flat, n, F, _lib.act_code(act), _stream()), "gcg_highway_bwd_f32")
+    return dP, dGpre, dHin
+
+
+def softmax_ce(logits, y=None, probs=None, grad=None, ce=None, hit=None, pred=None, denom=None):
+    """Output head on gathered logits -- gcg_softmax_ce_f32 (mlpconv.py:216,223,227-233,252)."""
+    L = _lib.lib()
+    lp, ldl = _mat(logits, "logits")
+    n, Cc = logits.shape
+    pp, ldp = (None, 0) if probs is None else _mat(probs, "probs")
+    gp, ldg = (None, 0) if grad is None else _mat(grad, "grad")
+    if pred is not None and pred.dtype != torch.int64:
+        raise TypeError("pred must be int64 (Theano argmax dtype)")
+    _lib.check(L.gcg_softmax_ce_f32(lp, ldl, _vec(y, "y", torch.int32), n, Cc,
+                                    float(denom if denom is not None else max(n, 1)), pp, ldp, gp, ldg,
+                                    _vec(ce, "ce"), _vec(hit, "hit"), _vec(pred, "pred", torch.int64),
+                                    _stream()), "gcg_softmax_ce_f32")
+
+
+def sum_scaled(x, scale=1.0, out=None):
+    if out is None:
+        out = torch.empty(1, dtype=torch.float32, device=x.device)
+    _lib.check(_lib.lib().gcg_sum_f32(_vec(x, "x"), x.numel(), float(scale), _vec(out, "out"), _stream()),
+               "gcg_sum_f32")
+    return out
+
+
+def scatter_rows(G, pos_ptr, pos_idx, n_rows, out=None):
+    L = _lib.lib()
+    gp, ldg = _mat(G, "G")
+    Cc = G.shape[1]
+    if out is None:
+        out = alloc_mat(n_rows, Cc, G.device)
+    op, ldo = _mat(out, "out")
+    _lib.check(L.gcg_scatter_rows_f32(gp, ldg, _vec(pos_ptr, "pos_ptr", torch.int32),
+                                      _vec(pos_idx, "pos_idx", torch.int32), n_rows, Cc, op, ldo, _stream()),
+               "gcg_scatter_rows_f32")
+    return out
+
+
+def gather_rows(X, idx, out=None):
+    L = _lib.lib()
+    xp, ldx = _mat(X, "X")
+    n, Cc = idx.numel(), X.shape[1]
+    if out is None:
+        out = alloc_mat(n, Cc, X.device)
+    op, ldo = _mat(out, "out")
+    _lib.check(L.gcg_gather_rows_f32(xp, ldx, _vec(idx, "idx", torch.int32), n, Cc, op, ldo, _stream()),
+               "gcg_gather_rows_f32")
+    return out
+
+
+def scatter_positions(idx, n_rows, device):
+    """CSR-like inverse of ``target_indices``: for node r the positions i with
+    idx[i] == r, ascending (host, once per index vector)."""
+    idx = np.asarray(idx, dtype=np.int64)
+    order = np.argsort(idx, kind="stable").astype(np.int32)
+    counts = np.bincount(idx, minlength=n_rows)
+    ptr = np.zeros(n_rows + 1, np.int32)
+    np.cumsum(counts, out=ptr[1:])
+    return torch.from_numpy(ptr).to(device), torch.from_numpy(order).to(device)
+
+
+# ---------------------------------------------------------------- optimiser
+class Adam:
+    """lasagne.updates.adam(lr=4e-3, 0.9, 0.999, 1e-8) (mlpconv.py:263) over a fixed
+    parameter list, one fused launch (gcg_adam_step_f32).  ``reg`` holds the
+    elastic-net coefficient per tensor (0 for biases; mlpconv.py:235-244)."""
+
+    def __init__(self, params, grads, reg, lr=4e-3, beta1=0.9, beta2=0.999, eps=1e-8):
+        self.params, self.grads = list(params), list(grads)
+        n = len(self.params)
+        for p, g in zip(self.params, self.grads):
+            if not (p.is_contiguous() and g.is_contiguous() and p.numel() == g.numel()):
+                raise ValueError("Adam needs contiguous parameters and gradients of equal size")
+        dev = self.params[0].device
+        self.m = [torch.zeros_like(p) for p in self.params]
+        self.v = [torch.zeros_like(p) for p in self.params]
+        self.t = torch.zeros(2, dtype=torch.float32, device=dev)     # [t, a_t]
+        self.reg_out = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.hyper = (float(lr), float(beta1), float(beta2), float(eps))
+        arr = lambda ts: (C.c_void_p * n)(*[t.data_ptr() for t in ts])
+        self._p, self._g, self._m, self._v = arr(self.params), arr(self.grads), arr(self.m), arr(self.v)
+        self._sizes = (C.c_int64 * n)(*[p.numel() for p in self.params])
+        self._reg = (C.c_float * n)(*[float(r) for r in reg])
+        self._n = n
+        self._wsbytes = int(_lib.lib().gcg_adam_workspace_bytes(n, self._sizes))
+        self._ws = torch.empty(max(self._wsbytes, 4), dtype=torch.uint8, device=dev)
+
+    def step(self):
+        lr, b1, b2, eps = self.hyper
+        _lib.check(_lib.lib().gcg_adam_step_f32(self._n, self._p, self._g, self._m, self._v, self._sizes,
+                                                self._reg, lr, b1, b2, eps, C.c_void_p(self.t.data_ptr()),
+                                                C.c_void_p(self.reg_out.data_ptr()),
+                                                C.c_void_p(self._ws.data_ptr()), self._ws.numel(), _stream()),
+                   "gcg_adam_step_f32")
+        return self.reg_out
+
+
+class ElasticNet:
+    """0.5*c*(|W|_1 + |W|_2^2) summed over a fixed tensor list (mlpconv.py:235-245),
+    for eval_loss where no update happens (gcg_elastic_net_f32)."""
+
+    def __init__(self, params, reg):
+        self.params = list(params)
+        n = len(self.params)
+        dev = self.params[0].device
+        self._p = (C.c_void_p * n)(*[t.data_ptr() for t in self.params])
+        self._sizes = (C.c_int64 * n)(*[p.numel() for p in self.params])
+        self._reg = (C.c_float * n)(*[float(r) for r in reg])
+        self._n = n
+        wsb = int(_lib.lib().gcg_adam_workspace_bytes(n, self._sizes))
+        self._ws = torch.empty(max(wsb, 4), dtype=torch.uint8, device=dev)
+        self.out = torch.zeros(1, dtype=torch.float32, device=dev)
+
+    def __call__(self):
+        _lib.check(_lib.lib().gcg_elastic_net_f32(self._n, self._p, self._sizes, self._reg,
+                                                  C.c_void_p(self.out.data_ptr()),
+                                                  C.c_void_p(self._ws.data_ptr()), self._ws.numel(), _stream()),
+                   "gcg_elastic_net_f32")
+        return self.out
+
+
+# ------------------------------------------------------------------- host
+def kdtree_fit(points, bucket_size):
+    """Region label per point (int64) and number of leaves -- gcg_kdtree_fit_host,
+    bit-exact restatement of kdtree.py:84-118,126-147."""
+    pts = np.ascontiguousarray(np.asarray(points, dtype=np.float64))
+    if pts.ndim != 2:
+        raise ValueError("points must be [n, dims]")
+    n, dims = pts.shape
+    labels = np.zeros(n, dtype=np.int64)
+    nl = C.c_int64(0)
+    _lib.check(_lib.lib().gcg_kdtree_fit_host(pts.ctypes.data_as(C.c_void_p), n, dims, int(bucket_size),
+                                              labels.ctypes.data_as(C.c_void_p), C.byref(nl)),
+               "gcg_kdtree_fit_host")
+    return labels, int(nl.value)
+
+
+def launch_count(reset=False):
+    L = _lib.lib()
+    n = int(L.gcg_launch_count())
+    if reset:
+        L.gcg_launch_count_reset()
+    return n

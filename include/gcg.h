@@ -1,0 +1,247 @@
+/*
+ * gcg.h -- C ABI of libgcg.so: the B200 (sm_100a) implementation of the
+ * graphconvgeo GCN propagation hot path.
+ *
+ * The reference (afcarl/graphconvgeo) has no FFI: its boundary for this path is
+ * the Lasagne Layer protocol (lasagne_layers.py:20-89) whose bodies call
+ * Theano's S.dot / T.dot.  Each entry point below replaces one of those calls
+ * (or the Theano-generated ops around it); the reference call site is cited
+ * per function.  graphconvgeo_b200/lasagne_layers.py re-creates the Layer
+ * classes on top of these functions via ctypes.
+ *
+ * Conventions
+ *   - every function returns 0 (GCG_OK) or a negative gcg_status; the message
+ *     is available from gcg_last_error() (thread-local).
+ *   - all matrices are float32 row-major with an explicit leading dimension
+ *     (in elements); CSR = (indptr int32[n_rows+1], indices int32[nnz],
+ *     vals float32[nnz]) with column indices sorted within a row.
+ *   - pointers named d_* / unprefixed data pointers are DEVICE pointers owned
+ *     by the caller (e.g. torch tensors); h_* are host pointers.  The library
+ *     never frees or retains caller memory beyond the call, except a
+ *     gcg_plan, which keeps the CSR device pointers it was created with (the
+ *     caller keeps them alive until gcg_plan_destroy).
+ *   - every device function is asynchronous on `stream` (a cudaStream_t passed
+ *     as void*), performs no allocation and no synchronisation, and is
+ *     therefore CUDA-graph capturable.  *_host functions run on the CPU.
+ */
+#ifndef GCG_H_
+#define GCG_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  GCG_OK = 0,
+  GCG_ERR_BAD_ARG = -1,
+  GCG_ERR_SHAPE = -2,
+  GCG_ERR_CUDA = -3,
+  GCG_ERR_NCCL = -4,
+  GCG_ERR_NOMEM = -5,
+  GCG_ERR_UNSUPPORTED = -6
+} gcg_status;
+
+/* non-linearities of the hot path (mlpconv.py:186-193; lang2loc.py:285-287) */
+typedef enum {
+  GCG_ACT_IDENTITY = 0,
+  GCG_ACT_RELU = 1,
+  GCG_ACT_TANH = 2,
+  GCG_ACT_SIGMOID = 3
+} gcg_act;
+
+/* dense contraction engines (gcg_gemm_f32 `mode`) */
+typedef enum {
+  GCG_GEMM_FMA = 0,     /* fp32 FFMA tiles                                   */
+  GCG_GEMM_TF32X3 = 1,  /* tcgen05 TF32 tensor cores, 3-term split (~fp32)   */
+  GCG_GEMM_TF32 = 2     /* tcgen05 TF32 single pass (10-bit mantissa inputs) */
+} gcg_gemm_mode;
+
+typedef struct gcg_plan gcg_plan; /* opaque: one per sparse matrix */
+
+int gcg_version(void);
+const char* gcg_last_error(void);
+/* number of kernels this library has launched in this process (bench.py's
+ * gpu_launches evidence); gcg_launch_count_reset() zeroes it. */
+int64_t gcg_launch_count(void);
+void gcg_launch_count_reset(void);
+
+/* ------------------------------------------------------------------ plans */
+
+/* Analyse a device CSR matrix once: finds the "long" rows (degree >
+ * long_row_threshold) of the power-law graph and cuts them into fixed-size
+ * segments so that no warp ever owns more than long_row_threshold non-zeros
+ * (deterministic two-pass reduction, no atomics).  h_indptr may be NULL, in
+ * which case indptr is copied back from the device (synchronous).
+ * Replaces: nothing in the reference (scipy needs no plan); it is the
+ * B200-side preparation for S.dot, lasagne_layers.py:26,65,67,84. */
+int gcg_plan_create_csr(int64_t n_rows, int64_t n_cols, int64_t nnz,
+                        const int32_t* d_indptr, const int32_t* d_indices,
+                        const float* d_vals, const int32_t* h_indptr,
+                        int32_t long_row_threshold, gcg_plan** out);
+int gcg_plan_destroy(gcg_plan* plan);
+/* bytes of scratch gcg_spmm_csr_f32 needs for an output of leading dim ldc */
+int64_t gcg_plan_workspace_bytes(const gcg_plan* plan, int64_t ldc);
+/* info[0..7] = n_rows, n_cols, nnz, n_long_rows, n_segments, max_degree,
+ *              long_row_threshold, reserved */
+int gcg_plan_info(const gcg_plan* plan, int64_t* info);
+
+/* ------------------------------------------------------------------- SpMM */
+
+/* C = epilogue( A . B )            A: the plan's CSR [n_rows, n_cols]
+ *   P    = A.B (+ C if accumulate)                    S.dot, lasagne_layers.py:26,65,67,84
+ *   Hc   = act(P + bias)                              :27-29, :69-71, :86-89
+ *   C    = gate ? gate*Hc + (1-gate)*carry : Hc       highway gate (north_star; not in reference)
+ *   conv_out (optional) also receives Hc when gating (needed by the backward).
+ * The same call serves the backward A^T.dP (A_hat is symmetric, so the forward
+ * plan is reused) and X^T.dZ (a plan of the transposed X).
+ * Per output element the products are summed in CSR order with separately
+ * rounded multiply and add, i.e. bit-identical to scipy's csr_matvecs for rows
+ * that are not split; split (long) rows differ only by summation order.
+ * B: [n_cols, F] ld ldb;  C: [n_rows, F] ld ldc.  The float4 path needs
+ * 16-byte aligned B/C and ldb, ldc multiples of 4 with ld >= round_up(F, 4)
+ * (pad columns of C are then overwritten with unspecified values); anything
+ * else takes the scalar path.
+ * panel_cols: 0 = whole rows per warp; >0 = process the feature dimension in
+ * column panels of that many floats, panel-major over the grid, so that one
+ * panel of B (n_cols*panel_cols*4 bytes) stays L2-resident while it is gathered.
+ * workspace: gcg_plan_workspace_bytes(plan, ldc) bytes (may be NULL if 0). */
+int gcg_spmm_csr_f32(const gcg_plan* plan, const float* B, int64_t ldb, int64_t F,
+                     float* C, int64_t ldc, const float* bias, int act,
+                     int accumulate, const float* gate, int64_t ld_gate,
+                     const float* carry, int64_t ld_carry, float* conv_out,
+                     int64_t ld_conv, int32_t panel_cols, void* workspace,
+                     int64_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------- GEMM */
+
+/* C = act( op(A).op(B) + beta*C + bias ) [ * act'(mask) ]
+ *   op(A): [M,K] (transA=0: stored [M,K] ld lda; transA=1: stored [K,M])
+ *   op(B): [K,N] (transB=0: stored [K,N] ld ldb; transB=1: stored [N,K])
+ * Replaces T.dot (lasagne_layers.py:82) and its two gradient products
+ * (dW = H^T.dZ, dH = dZ.W^T) that theano.grad derives (mlpconv.py:263).
+ * mask (optional, [M,N] ld ld_mask): multiplies the result by mask_act'(mask)
+ * expressed from the activation OUTPUT (relu: mask>0; tanh: 1-mask^2) -- fuses
+ * dP = dA * act'(.) into the producer of dA.
+ * split_k > 1 cuts K into that many slices reduced in a fixed order
+ * (deterministic); workspace must then hold split_k*M*N floats. 0 = auto. */
+int gcg_gemm_f32(int transA, int transB, int64_t M, int64_t N, int64_t K,
+                 const float* A, int64_t lda, const float* B, int64_t ldb,
+                 float* C, int64_t ldc, float beta, const float* bias, int act,
+                 const float* mask, int64_t ld_mask, int mask_act, int mode,
+                 int32_t split_k, void* workspace, int64_t workspace_bytes,
+                 void* stream);
+int64_t gcg_gemm_workspace_bytes(int transA, int transB, int64_t M, int64_t N,
+                                 int64_t K, int mode, int32_t split_k);
+
+/* ------------------------------------------------- epilogues / reductions */
+
+/* out[j] = sum_i X[i,j]   (db = colsum(dP); bias grads of lasagne_layers.py:27-28,69-70,86-87)
+ * deterministic two-pass; workspace >= gcg_colsum_workspace_bytes(n_rows, F). */
+int gcg_colsum_f32(const float* X, int64_t ld, int64_t n_rows, int64_t F, float* out,
+                   void* workspace, int64_t workspace_bytes, void* stream);
+int64_t gcg_colsum_workspace_bytes(int64_t n_rows, int64_t F);
+
+/* dP = dA * act'(A) (from the activation output A), optionally in place (dP == dA).
+ * Backward of the non-linearity at lasagne_layers.py:29,71,89. */
+int gcg_act_bwd_f32(const float* dA, int64_t ld_da, const float* A, int64_t ld_a,
+                    float* dP, int64_t ld_dp, int64_t n_rows, int64_t F, int act,
+                    void* stream);
+
+/* Backward of the highway mix  O = g*Hc + (1-g)*Hin,  Hc = act(P):
+ *   dP    = g*dO * act'(Hc)          dGpre = dO*(Hc-Hin) * g*(1-g)
+ *   dHin  = (1-g)*dO                 (all [n_rows,F]; any output may alias dO)
+ * north_star formula; not in the reference. */
+int gcg_highway_bwd_f32(const float* dO, int64_t ld_do, const float* g, int64_t ld_g,
+                        const float* Hc, int64_t ld_hc, const float* Hin, int64_t ld_hin,
+                        float* dP, int64_t ld_dp, float* dGpre, int64_t ld_dg,
+                        float* dHin, int64_t ld_dh, int64_t n_rows, int64_t F, int act,
+                        void* stream);
+
+/* Output head on the gathered logits L [n_idx, C] (mlpconv.py:216,223,227-233,252):
+ *   probs = softmax_rows(L) (max-subtracted);  ce[i] = -log probs[i, y[i]];
+ *   pred[i] = argmax (first maximum, like np.argmax);  hit[i] = (pred[i]==y[i]);
+ *   G = (probs - onehot(y)) / denom   (gradient of mean CE w.r.t. L; denom = n_idx)
+ * probs / G / ce / hit / pred may each be NULL.  y may be NULL when only
+ * probs / pred are wanted (predict / predict_proba, mlpconv.py:320-336). */
+int gcg_softmax_ce_f32(const float* L, int64_t ld_l, const int32_t* y, int64_t n_idx,
+                       int64_t C, float denom, float* probs, int64_t ld_p, float* G,
+                       int64_t ld_g, float* ce, float* hit, int64_t* pred, void* stream);
+
+/* out[0] = scale * sum(x[0..n))  -- deterministic (fixed tree), single block. */
+int gcg_sum_f32(const float* x, int64_t n, float scale, float* out, void* stream);
+
+/* dP[r,:] = sum over the positions p in pos_idx[pos_ptr[r] .. pos_ptr[r+1]) of G[p,:]
+ * (zero where a node has no target position).  Deterministic scatter-ADD that is
+ * the gradient of the row gather activation[target_indices,:] (lasagne_layers.py:88);
+ * duplicates in target_indices accumulate (tensormain.py:226 samples with replacement). */
+int gcg_scatter_rows_f32(const float* G, int64_t ld_g, const int32_t* pos_ptr,
+                         const int32_t* pos_idx, int64_t n_rows, int64_t C, float* dP,
+                         int64_t ld_dp, void* stream);
+/* out[i,:] = X[idx[i],:]  (lasagne_layers.py:88) */
+int gcg_gather_rows_f32(const float* X, int64_t ld_x, const int32_t* idx, int64_t n_idx,
+                        int64_t C, float* out, int64_t ld_out, void* stream);
+
+/* ---------------------------------------------------------------- optimiser */
+
+/* One fused multi-tensor step of lasagne.updates.adam (mlpconv.py:263) with the
+ * elastic-net sub-gradient of mlpconv.py:235-244 folded in:
+ *   g' = g + reg_coef[k]*0.5*(sign(p) + 2p);  m,v update;  p -= a_t*m/(sqrt(v)+eps)
+ * where a_t = lr*sqrt(1-b2^t)/(1-b1^t) is computed on the DEVICE from the step
+ * state d_t (float32[2]: d_t[0] = step counter t, incremented by this call;
+ * d_t[1] = a_t, written by this call) so the step is CUDA-graph replayable.
+ * reg_out (optional, float[1]): receives sum_k reg_coef[k]*0.5*(|p|_1 + |p|_2^2) of
+ * the PRE-update parameters (the penalty term of the loss f_train returns).
+ * h_params/h_grads/h_m/h_v: host arrays of n_tensors device pointers; h_sizes: element
+ * counts (tensors must be contiguous); h_reg: per-tensor coefficient (0 for biases).
+ * workspace >= gcg_adam_workspace_bytes(n_tensors, h_sizes). */
+int gcg_adam_step_f32(int32_t n_tensors, float* const* h_params, const float* const* h_grads,
+                      float* const* h_m, float* const* h_v, const int64_t* h_sizes,
+                      const float* h_reg, float lr, float beta1, float beta2, float eps,
+                      float* d_t, float* reg_out, void* workspace, int64_t workspace_bytes,
+                      void* stream);
+int64_t gcg_adam_workspace_bytes(int32_t n_tensors, const int64_t* h_sizes);
+
+/* out[0] = sum_k h_reg[k]*0.5*(|p_k|_1 + |p_k|_2^2): the elastic-net penalty of
+ * mlpconv.py:235-245 alone (eval_loss of f_val adds it without an update).
+ * workspace >= gcg_adam_workspace_bytes(n_tensors, h_sizes). */
+int gcg_elastic_net_f32(int32_t n_tensors, const float* const* h_params, const int64_t* h_sizes,
+                        const float* h_reg, float* out, void* workspace, int64_t workspace_bytes,
+                        void* stream);
+
+/* --------------------------------------------------------------- host side */
+
+/* k-d tree region labels, bit-exact restatement of kdtree.py:84-118,126-147
+ * (float64 compares, np.median split, left-before-right leaf numbering). */
+int gcg_kdtree_fit_host(const double* h_points, int64_t n, int32_t dims, int64_t bucket_size,
+                        int64_t* h_labels, int64_t* n_leaves);
+
+/* A_hat = D^-1/2 (A, unit diagonal) D^-1/2 in float64, cast to float32 --
+ * tensormain.py:170-180,221.  Input: CSR pattern of the adjacency (sorted
+ * columns; weights NULL = binary).  Call gcg_ahat_nnz_host first to size the
+ * outputs (rows lacking a diagonal entry gain one). */
+int64_t gcg_ahat_nnz_host(int64_t n, const int32_t* h_indptr, const int32_t* h_indices);
+int gcg_ahat_build_host(int64_t n, const int32_t* h_indptr, const int32_t* h_indices,
+                        const double* h_weights, int32_t* out_indptr, int32_t* out_indices,
+                        float* out_vals);
+
+/* CSR transpose (stable: rows ascending inside each output row), used once per
+ * fit to build X^T for dW1 = X^T.dZ1 (Dot.grad of lasagne_layers.py:26,65). */
+int gcg_csr_transpose_host(int64_t n_rows, int64_t n_cols, const int32_t* h_indptr,
+                           const int32_t* h_indices, const float* h_vals, int32_t* t_indptr,
+                           int32_t* t_indices, float* t_vals);
+
+/* out CSR = rows idx[0..n_idx) of the input CSR (duplicates allowed).  Used to turn
+ * activation[target_indices,:] of a propagated matrix into a propagation with
+ * A_hat[target_indices,:] so that only the wanted rows are ever computed.
+ * Two-call protocol: out_indices == NULL returns the nnz needed. */
+int64_t gcg_csr_gather_rows_host(int64_t n_rows, const int32_t* h_indptr,
+                                 const int32_t* h_indices, const float* h_vals,
+                                 const int32_t* idx, int64_t n_idx, int32_t* out_indptr,
+                                 int32_t* out_indices, float* out_vals);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GCG_H_ */

@@ -1,0 +1,21 @@
+"""CPU oracle for the graphconvgeo GCN propagation hot path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing in ``graphconvgeo_b200`` may import this
+package; only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s
+``cpu_baseline`` / ``--impl reference`` legs do, and there only as the checker
+or the CPU comparator, never as the product path.
+
+Parity status (see DESIGN.md "Oracle"):
+
+* GCN layers / loss / backward / Adam (``gcn_oracle.py``): **parity unpinned by
+  the reference** -- the reference ships no tests, golden vectors or fixtures
+  and its own executable (Python 2 + Theano + Lasagne) cannot run in this
+  image.  The restatement follows the reference source line by line (each
+  function cites file:line) and is cross-checked against torch-CPU autograd.
+* Highway gate: **parity unpinned** -- the gate is not in the reference at all;
+  the oracle restates the formula given in BASELINE.json's ``north_star``.
+* kd-tree labels (``kdtree_oracle.py``): **pinned** -- checked bit-for-bit
+  against the reference's own ``kdtree.py`` (imported from /root/reference by
+  ``tests/golden/make_kdtree_golden.py``, outputs committed under
+  ``tests/golden/``).
+"""
