@@ -1,0 +1,366 @@
+#!/usr/bin/env python
+"""bench.py -- GCN fwd+bwd epoch time and A_hat.H SpMM HBM GB/s on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload twitter-world|twitter-us|geotext]
+    python bench.py --impl reference ...      # the reference's CPU path (oracle port) on host cores
+    torchrun ... bench.py --gpus N ...        # one rank per GPU, row-partitioned A_hat
+
+A "step" is one epoch: one f_train call = full-graph forward + backward + Adam step
+(mlpconv.py:293-295) of the 3-layer highway GCN on a seeded synthetic workload of the named
+shape.  `value` is device time per epoch with inputs resident in HBM; `e2e` re-uploads the
+epoch's host inputs (X CSR, labels, target indices -- what f_train(X, Y, idx) receives) from
+pinned memory and reads loss/acc back every step.  `roofline` is the A_hat.H SpMM kernel
+(algorithmic bytes 8*nnz + 4*(N+1) + 8*N*F over its CUDA-event time).  One JSON line on stdout.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------ clocks
+class ClockSampler:
+    """SM clock / throttle reasons sampled every 200 ms while the timed region runs."""
+
+    def __init__(self, index=0):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:            # pragma: no cover
+            self.nv = None
+            log("clock sampler unavailable:", e)
+
+    def _run(self):
+        nv = self.nv
+        names = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                 "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                 "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------ CPU baseline
+def cpu_reference_epoch(workload, n_layers, highway, scale, epochs=1, threads=None):
+    """The reference's CPU path (oracle port: scipy csr@dense + BLAS, float32) on a bounded sample
+    of the workload: the same shape generator at `scale` of the node/vocabulary counts.  Returns
+    (ms per epoch on the sample, description, threads)."""
+    from graphconvgeo_b200 import synth
+    from oracle import gcn_oracle as go
+    threads = threads or os.cpu_count()
+    w = synth.make_workload(workload, scale=scale)
+    rng = np.random.RandomState(0)
+    params = go.init_params(rng, w.X.shape[1], w.hidden, w.n_classes, n_layers, highway)
+    net = go.GCNOracle(w.X, w.A_hat, n_layers, highway, (1e-6, 1e-6))
+    y = w.Y[w.train_indices].astype(np.int32)
+    st = go.AdamState(params)
+    best = None
+    for _ in range(epochs):
+        t0 = time.perf_counter()
+        loss, acc, grads, _c = net.loss_and_grads(params, w.train_indices, y)
+        go.adam_step(params, grads, st)
+        dt = (time.perf_counter() - t0) * 1e3
+        best = dt if best is None else min(best, dt)
+    desc = ("1 epoch of the oracle port (scipy csr@dense 1 thread + BLAS %d threads) on the %s generator at "
+            "scale %.4g: %d nodes, vocab %d, nnzA %d, nnzX %d; value = sample ms / scale"
+            % (threads, workload, scale, w.meta["n"], w.X.shape[1], w.meta["nnz_A"], w.meta["nnz_X"]))
+    return best, desc, threads
+
+
+CPU_SCALE = {"twitter-world": 1.0 / 64, "twitter-us": 1.0 / 24, "geotext": 1.0, "tiny": 1.0}
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path (oracle port; Theano is not
+    installable here) on the box's host cores, bounded sample, same metric/unit/config."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    scale = CPU_SCALE[args.workload]
+    times = []
+    for i in range(args.warmup + args.steps):
+        ms, desc, threads = cpu_reference_epoch(args.workload, args.layers, bool(args.highway), scale, epochs=1)
+        if i >= args.warmup:
+            times.append(ms)
+        if sum(times) > 150e3:
+            break
+    ms = float(np.mean(times)) / scale
+    line = {
+        "impl": "reference", "metric": "gcn_fwd_bwd_epoch_ms", "value": ms, "unit": "ms", "n_gpus": args.gpus,
+        "steps": len(times), "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": False,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": bench_config(args),
+        "cpu_baseline": {"value": ms, "unit": "ms", "cores": threads, "kind": "port", "sample": desc},
+        "e2e": {"value": ms, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def bench_config(args):
+    return {"workload": "%s-shaped synthetic, %d-layer %sGCN, full-batch fwd+bwd+Adam epoch"
+                        % (args.workload, args.layers, "highway " if args.highway else ""),
+            "n_layers": args.layers, "highway": bool(args.highway),
+            "l2": "flush" if args.workload in ("geotext", "tiny") else "inputs larger than L2"}
+
+
+# ------------------------------------------------------------------ GPU arm
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from graphconvgeo_b200 import ops, synth
+    from graphconvgeo_b200.mlpconv import MLPCONV
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torchrun --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    t0 = time.time()
+    wl = synth.make_workload_device(args.workload, device=dev, seed=77, community=not args.random_graph)
+    log("[rank %d] workload %s built in %.1fs: %s" % (rank, args.workload, time.time() - t0, wl.meta))
+
+    model_kwargs = dict(n_epochs=args.steps, regul_coefs=[1e-6, 1e-6], hidden_layer_size=wl.hidden, drop_out=False,
+                        n_layers=args.layers, highway=bool(args.highway), seed=1, device=dev, cuda_graph=True)
+    if world > 1:
+        from graphconvgeo_b200.dist import DistMLPCONV
+        m = DistMLPCONV(**model_kwargs)
+    else:
+        m = MLPCONV(**model_kwargs)
+    t0 = time.time()
+    m.prepare(wl.X, wl.train_indices, wl.dev_indices, wl.test_indices, wl.Y, wl.A_hat)
+    log("[rank %d] model prepared in %.1fs" % (rank, time.time() - t0))
+
+    flush = None
+    if bench_config(args)["l2"] == "flush":
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---------------- warm-up (epoch 1 eager, then graph capture, then replays)
+    for _ in range(max(args.warmup, 3)):
+        m.f_train()
+    barrier()
+    ops.launch_count(reset=True)
+    launches_per_step = m.launches_per_step if hasattr(m, "launches_per_step") else None
+
+    # ---------------- timed region: exactly K epochs, device time, max over ranks
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    sampler = ClockSampler(local)
+    barrier()
+    with sampler:
+        for s, e in ev:
+            if flush is not None:
+                flush.fill_(1)
+            s.record()
+            m.f_train()
+            e.record()
+        barrier()
+    step_ms = [s.elapsed_time(e) for s, e in ev]
+    total_ms = float(sum(step_ms))
+    if world > 1:
+        t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    loss, acc = m.train_results()
+    log("[rank %d] epoch %.3f ms (min %.3f max %.3f) loss %.5f acc %.4f" % (rank, ms_per_step, min(step_ms), max(step_ms), loss, acc))
+
+    # ---------------- kernel launches per epoch (counted eagerly, once)
+    m_graph, m._graph = m._graph, None
+    ops.launch_count(reset=True)
+    m._train_step_enqueue()
+    torch.cuda.synchronize(dev)
+    launches = ops.launch_count(reset=True)
+    m._graph = m_graph
+
+    # ---------------- e2e: host inputs re-uploaded every epoch, loss/acc read back
+    e2e = None
+    if world == 1:
+        e2e = measure_e2e(m, args, dev, flush)
+
+    # ---------------- roofline of the headline kernel: A_hat . H  (F = hidden)
+    roof = spmm_roofline(m, wl, dev) if rank == 0 else None
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        scale = CPU_SCALE[args.workload]
+        ms, desc, threads = cpu_reference_epoch(args.workload, args.layers, bool(args.highway), scale, epochs=1)
+        cpu = {"value": ms / scale, "unit": "ms", "cores": threads, "kind": "port", "sample": desc,
+               "sample_ms": ms}
+
+    line = {
+        "metric": "gcn_fwd_bwd_epoch_ms", "value": ms_per_step, "unit": "ms", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": False, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": dict(bench_config(args), nodes=wl.meta["n"], vocab=wl.meta["vocab"], hidden=wl.hidden,
+                       regions=wl.n_classes, nnz_A=wl.meta["nnz_A"], nnz_X=wl.meta["nnz_X"],
+                       max_degree=wl.meta["max_degree"], graph="community" if wl.meta["community"] else "chung-lu",
+                       parallelism="row-partition x%d" % world if world > 1 else "single GPU",
+                       gemm_mode=os.environ.get("GCG_GEMM_MODE", "auto")),
+        "clocks": sampler.summary(), "gpu_launches": launches * args.steps,
+        "launches_per_epoch": launches, "loss": loss, "acc": acc,
+    }
+    if e2e is not None:
+        line["e2e"] = e2e
+    if roof is not None:
+        line["roofline"] = roof["roofline"]
+        line["spmm"] = roof["detail"]
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def measure_e2e(m, args, dev, flush):
+    """Epoch through the public call with HOST inputs: X (CSR), Y_train, train_indices are copied from
+    pinned host memory every step (Theano copies f_train's inputs per call, mlpconv.py:295) and the
+    step's [loss, acc] are read back."""
+    import torch
+    X = m.Xd
+    host = [t.cpu().pin_memory() for t in (X.indptr, X.indices, X.data, m.y_train_dev, m.ti_train.dev)]
+    devt = [X.indptr, X.indices, X.data, m.y_train_dev, m.ti_train.dev]
+    h2d = int(sum(t.numel() * t.element_size() for t in host))
+    out_host = torch.empty(3, dtype=torch.float32).pin_memory()
+    steps = max(3, min(args.steps, 10))
+    times = []
+    for i in range(steps + 2):
+        if flush is not None:
+            flush.fill_(1)
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for d, h in zip(devt, host):
+            d.copy_(h, non_blocking=True)
+        hb = m.f_train()
+        out_host[0:2].copy_(hb["out"], non_blocking=True)
+        out_host[2:3].copy_(m.adam.reg_out, non_blocking=True)
+        e.record()
+        e.synchronize()
+        if i >= 2:
+            times.append(s.elapsed_time(e))
+    return {"value": float(np.mean(times)), "unit": "ms", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 12,
+            "steps": steps}
+
+
+def spmm_roofline(m, wl, dev, reps=10):
+    """A_hat . H at F = hidden on the epoch's own operands, CUDA events around each launch."""
+    import torch
+    from graphconvgeo_b200 import ops
+    peak, peak_src = measured_peaks()
+    A = m.l_hid1.H
+    H = m.l_hid1._out
+    N, F = H.shape
+    out = ops.alloc_mat(N, F, dev)
+    nnz = A.nnz
+    alg_bytes = 8 * nnz + 4 * (N + 1) + 8 * N * F
+    results = {}
+    for label, panel in (("auto", None), ("rows", 0)):
+        for _ in range(3):
+            ops.spmm(A, H, out=out, panel_cols=panel)
+        ts = []
+        for _ in range(reps):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            ops.spmm(A, H, out=out, panel_cols=panel)
+            e.record()
+            e.synchronize()
+            ts.append(s.elapsed_time(e))
+        results[label] = float(np.mean(ts))
+    t_ms = results["auto"]
+    achieved = alg_bytes / (t_ms * 1e-3) / 1e9
+    gather_model = (8 * nnz + 4 * nnz * F + 4 * N * F) / (t_ms * 1e-3) / 1e9
+    return {"roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "spmm_vec_kernel (A_hat.H, F=%d)" % F,
+                         "algorithmic_bytes": alg_bytes, "ms": t_ms, "peak_source": peak_src,
+                         "frac_of_nominal_8000": achieved / 8000.0},
+            "detail": {"N": N, "F": F, "nnz": nnz, "ms_auto_panel": results["auto"], "ms_whole_rows": results["rows"],
+                       "panel_cols_auto": ops.auto_panel_cols(N, F), "gather_model_GBps": gather_model,
+                       "plan": A.plan_info()}}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="twitter-world", choices=["twitter-world", "twitter-us", "geotext", "tiny"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--layers", type=int, default=3)
+    ap.add_argument("--highway", type=int, default=1)
+    ap.add_argument("--random-graph", action="store_true", help="Chung-Lu graph without community structure")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -193,3 +193,121 @@ def make_workload(name="geotext", seed=77, community=True, scale=1.0, **override
         locs=locs, medians=med, hidden=cfg["hidden"], n_classes=int(Y.max()) + 1,
         meta=dict(cfg, n=n, nnz_A=int(a_hat.nnz), nnz_X=int(X.nnz), seed=seed, community=community,
                   max_degree=int(np.diff(a_hat.indptr).max())))
+
+
+# --------------------------------------------------------------------------- #
+# Large workloads: the same generators written with torch ops so that the 1.4M-node
+# Twitter-World shape is produced on the GPU in seconds (NumPy on 8 host cores needs
+# ~8 minutes).  Data generation is plumbing, not the product; the arrays are then
+# handed to the product exactly like host data would be.
+# --------------------------------------------------------------------------- #
+def _torch_graph(n, avg_deg, gen, device, city=None, intra=0.8, alpha=1.5):
+    import torch
+    m = int(n * avg_deg / 2)
+    u = torch.rand(n, generator=gen, device=device, dtype=torch.float64)
+    w = (1.0 - u).pow(-1.0 / alpha)                       # Pareto(alpha) + 1
+    cdf = torch.cumsum(w, 0)
+    cdf = cdf / cdf[-1]
+    src = torch.searchsorted(cdf, torch.rand(m, generator=gen, device=device, dtype=torch.float64)).clamp_(max=n - 1)
+    dst = torch.randint(0, n, (m,), generator=gen, device=device)
+    if city is not None:
+        order = torch.argsort(city, stable=True)
+        sorted_c = city[order]
+        starts = torch.searchsorted(sorted_c, sorted_c, right=False)
+        ends = torch.searchsorted(sorted_c, sorted_c, right=True)
+        pos_of = torch.empty(n, dtype=torch.int64, device=device)
+        pos_of[order] = torch.arange(n, device=device)
+        sp_ = pos_of[src]
+        lo, hi = starts[sp_], ends[sp_]
+        r = torch.rand(m, generator=gen, device=device, dtype=torch.float64)
+        local = order[lo + (r * (hi - lo).double()).long().clamp_(max=n)]
+        use_local = torch.rand(m, generator=gen, device=device) < intra
+        dst = torch.where(use_local, local, dst)
+    keep = src != dst
+    src, dst = src[keep], dst[keep]
+    a, b = torch.minimum(src, dst), torch.maximum(src, dst)
+    key = torch.unique(a * n + b)
+    a, b = key // n, key % n
+    rows = torch.cat([a, b])
+    cols = torch.cat([b, a])
+    key = torch.sort(rows * n + cols).values
+    rows, cols = key // n, key % n
+    indptr = torch.zeros(n + 1, dtype=torch.int64, device=device)
+    indptr[1:] = torch.cumsum(torch.bincount(rows, minlength=n), 0)
+    return indptr.to(torch.int32), cols.to(torch.int32)
+
+
+def _torch_tfidf(n, vocab, mean_terms, gen, device, zipf_s=1.1):
+    import torch
+    sigma = 0.6
+    mu = float(np.log(mean_terms) - 0.5 * sigma * sigma)
+    lens = torch.exp(mu + sigma * torch.randn(n, generator=gen, device=device, dtype=torch.float64))
+    lens = lens.clamp_(min=1, max=vocab // 2).long()
+    total = int(lens.sum().item())
+    ranks = torch.arange(1, vocab + 1, dtype=torch.float64, device=device)
+    cdf = torch.cumsum(ranks.pow(-zipf_s), 0)
+    cdf = cdf / cdf[-1]
+    rows = torch.repeat_interleave(torch.arange(n, device=device), lens)
+    keys = []
+    step = 1 << 26                                          # bound peak memory
+    for s in range(0, total, step):
+        e = min(total, s + step)
+        c = torch.searchsorted(cdf, torch.rand(e - s, generator=gen, device=device, dtype=torch.float64)).clamp_(max=vocab - 1)
+        keys.append(rows[s:e] * vocab + c)
+    del rows
+    key = torch.unique(torch.cat(keys))
+    del keys
+    rows, cols = key // vocab, key % vocab
+    del key
+    df = torch.bincount(cols, minlength=vocab).double()
+    idf = torch.log((1.0 + n) / (1.0 + df)) + 1.0
+    vals = idf[cols]
+    sq = torch.zeros(n, dtype=torch.float64, device=device).index_add_(0, rows, vals * vals)
+    vals = (vals / torch.sqrt(sq[rows])).float()
+    indptr = torch.zeros(n + 1, dtype=torch.int64, device=device)
+    indptr[1:] = torch.cumsum(torch.bincount(rows, minlength=n), 0)
+    return indptr.to(torch.int32), cols.to(torch.int32), vals
+
+
+def make_workload_device(name="twitter-world", device="cuda", seed=77, community=True, scale=1.0, **overrides):
+    """Same shapes as make_workload, generated with torch on ``device``.  Returns a Workload whose
+    X / A_hat are ``CSRMatrix`` objects already resident on the device (their host copies are
+    materialised lazily, only where the product needs them: transposes and row gathers)."""
+    import torch
+    from . import ops
+    from .sparse import CSRMatrix, _np_ptr
+    from . import _lib
+    cfg = dict(WORKLOADS[name])
+    cfg.update(overrides)
+    if scale != 1.0:
+        for k in ("n_train", "n_dev", "n_test", "vocab"):
+            cfg[k] = max(8, int(round(cfg[k] * scale)))
+        cfg["n_cities"] = max(4, int(round(cfg["n_cities"] * max(scale, 0.05))))
+    n_train, n_dev, n_test = cfg["n_train"], cfg["n_dev"], cfg["n_test"]
+    n = n_train + n_dev + n_test
+    dev = torch.device(device)
+    gen = torch.Generator(device=dev).manual_seed(seed)
+    locs, city = city_locations(n, cfg["n_cities"], seed)
+    city_t = torch.from_numpy(city).to(dev) if community else None
+    ip, ix = _torch_graph(n, cfg["avg_deg"], gen, dev, city=city_t)
+    # A_hat through the product's host builder (gcg_ahat_build_host): float64 normalise, cast
+    hip, hix = ip.cpu().numpy(), ix.cpu().numpy()
+    L = _lib.lib()
+    nnz = L.gcg_ahat_nnz_host(n, _np_ptr(hip), _np_ptr(hix))
+    oip, oix, ov = np.empty(n + 1, np.int32), np.empty(nnz, np.int32), np.empty(nnz, np.float32)
+    _lib.check(L.gcg_ahat_build_host(n, _np_ptr(hip), _np_ptr(hix), None, _np_ptr(oip), _np_ptr(oix), _np_ptr(ov)),
+               "gcg_ahat_build_host")
+    a_hat = CSRMatrix.from_host((oip, oix, ov), (n, n), dev)
+    del ip, ix
+    xip, xix, xv = _torch_tfidf(n, cfg["vocab"], cfg["terms"], gen, dev)
+    X = CSRMatrix(xip, xix, xv, (n, cfg["vocab"]), long_row_threshold=1024)
+    y_train, y_other, med = assign_classes(locs[:n_train], locs[n_train:], cfg["bucket"])
+    Y = np.concatenate([y_train, y_other]).astype(np.int64)
+    return Workload(
+        name=name, X=X, A_hat=a_hat, Y=Y,
+        train_indices=np.arange(0, n_train, dtype=np.int32),
+        dev_indices=np.arange(n_train, n_train + n_dev, dtype=np.int32),
+        test_indices=np.arange(n_train + n_dev, n, dtype=np.int32),
+        locs=locs, medians=med, hidden=cfg["hidden"], n_classes=int(Y.max()) + 1,
+        meta=dict(cfg, n=n, nnz_A=int(a_hat.nnz), nnz_X=int(X.nnz), seed=seed, community=community,
+                  max_degree=int(np.diff(oip).max())))

@@ -1,0 +1,92 @@
+"""Dense projections (gcg_gemm_f32) against NumPy: T.dot of lasagne_layers.py:82 and the two
+gradient products theano.grad derives from it."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from util import assert_close, to_dev  # noqa: E402
+
+MODES = ["fma"]
+
+
+def tc_modes():
+    from graphconvgeo_b200 import _lib
+    L = _lib.lib()
+    if hasattr(L, "gcg_gemm_tc_available") and L.gcg_gemm_tc_available():
+        return ["fma", "tf32x3"]
+    return ["fma"]
+
+
+def ref_gemm(A, B, ta, tb):
+    a = A.T if ta else A
+    b = B.T if tb else B
+    return (a.astype(np.float64) @ b.astype(np.float64))
+
+
+@pytest.mark.parametrize("ta,tb", [(False, False), (True, False), (False, True), (True, True)])
+@pytest.mark.parametrize("M,N,K", [(1, 1, 1), (128, 128, 16), (130, 70, 33), (257, 300, 600), (1000, 930, 300),
+                                   (64, 1024, 77), (300, 128, 5000)])
+def test_gemm_shapes(ta, tb, M, N, K):
+    from graphconvgeo_b200 import ops
+    rng = np.random.RandomState(M + N + K)
+    s = 1.0 / np.sqrt(K)
+    A = (rng.standard_normal((K, M) if ta else (M, K)) * s).astype(np.float32)
+    B = rng.standard_normal((N, K) if tb else (K, N)).astype(np.float32)
+    for mode in tc_modes():
+        got = ops.gemm(to_dev(A), to_dev(B), transA=ta, transB=tb, mode=mode).cpu().numpy()
+        assert_close(got, ref_gemm(A, B, ta, tb), atol=5e-6, what="%s %s" % (mode, (ta, tb, M, N, K)))
+
+
+def test_gemm_epilogues_beta_bias_act_mask():
+    from graphconvgeo_b200 import ops
+    rng = np.random.RandomState(0)
+    M, N, K = 300, 200, 150
+    A = (rng.standard_normal((M, K)) / np.sqrt(K)).astype(np.float32)
+    B = rng.standard_normal((K, N)).astype(np.float32)
+    C0 = rng.standard_normal((M, N)).astype(np.float32)
+    bias = rng.standard_normal(N).astype(np.float32)
+    mask = rng.standard_normal((M, N)).astype(np.float32)
+    for mode in tc_modes():
+        out = to_dev(C0)
+        ops.gemm(to_dev(A), to_dev(B), out=out, beta=1.0, bias=to_dev(bias), act="sigmoid", mode=mode)
+        ref = 1.0 / (1.0 + np.exp(-(A.astype(np.float64) @ B + C0 + bias)))
+        assert_close(out.cpu().numpy(), ref, atol=2e-6, what=mode)
+        out = ops.gemm(to_dev(A), to_dev(B), mask=to_dev(mask), mask_act="rectify", mode=mode)
+        assert_close(out.cpu().numpy(), (A.astype(np.float64) @ B) * (mask > 0), atol=5e-6, what=mode)
+        out = ops.gemm(to_dev(A), to_dev(B), mask=to_dev(np.tanh(mask)), mask_act="tanh", mode=mode)
+        assert_close(out.cpu().numpy(), (A.astype(np.float64) @ B) * (1 - np.tanh(mask) ** 2), atol=5e-6, what=mode)
+
+
+@pytest.mark.parametrize("split", [0, 1, 3, 16])
+def test_split_k_is_deterministic_and_correct(split):
+    """dW = H^T.dZ: tall-skinny reduction over the node dimension."""
+    from graphconvgeo_b200 import ops
+    rng = np.random.RandomState(1)
+    K, M, N = 20000, 96, 40
+    A = (rng.standard_normal((K, M)) * 0.05).astype(np.float32)
+    B = (rng.standard_normal((K, N)) * 0.05).astype(np.float32)
+    Ad, Bd = to_dev(A), to_dev(B)
+    g1 = ops.gemm(Ad, Bd, transA=True, split_k=split, mode="fma").cpu().numpy()
+    g2 = ops.gemm(Ad, Bd, transA=True, split_k=split, mode="fma").cpu().numpy()
+    assert np.array_equal(g1, g2)
+    assert_close(g1, A.astype(np.float64).T @ B.astype(np.float64), atol=3e-6)
+
+
+def test_unaligned_leading_dimensions():
+    from graphconvgeo_b200 import ops
+    rng = np.random.RandomState(2)
+    A = torch.from_numpy((rng.standard_normal((50, 37)) * 0.1).astype(np.float32)).cuda()     # ld 37
+    B = torch.from_numpy(rng.standard_normal((37, 29)).astype(np.float32)).cuda()             # ld 29
+    out = torch.empty(50, 29, device="cuda")
+    ops.gemm(A, B, out=out, mode="fma")
+    assert_close(out.cpu().numpy(), A.cpu().numpy().astype(np.float64) @ B.cpu().numpy(), atol=3e-6)
+
+
+def test_errors():
+    from graphconvgeo_b200 import ops
+    with pytest.raises(ValueError):
+        ops.gemm(torch.zeros(4, 5, device="cuda"), torch.zeros(6, 3, device="cuda"))
+    with pytest.raises(TypeError):
+        ops.gemm(torch.zeros(4, 5), torch.zeros(5, 3))

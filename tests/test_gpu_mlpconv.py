@@ -1,0 +1,172 @@
+"""End-to-end parity of the GCN (MLPCONV, mlpconv.py:121-346) with the oracle: per-layer
+activations and gradients within 1e-6 + 1e-4*|ref| (north_star), identical argmax except
+exact ties, a multi-step Adam trajectory, CUDA-graph replay == eager, and fit()."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from oracle import gcn_oracle as go  # noqa: E402
+from util import assert_close  # noqa: E402
+
+
+def workload(name="tiny", **kw):
+    from graphconvgeo_b200 import synth
+    return synth.make_workload(name, **kw)
+
+
+def make_model(w, n_layers, highway, params, idx, cuda_graph=False, act="rectify", reg=(1e-4, 2e-4)):
+    from graphconvgeo_b200.mlpconv import MLPCONV
+    m = MLPCONV(n_epochs=1, regul_coefs=list(reg), hidden_layer_size=w.hidden, drop_out=False,
+                n_layers=n_layers, highway=highway, init_parameters=[p.copy() for p in params],
+                cuda_graph=cuda_graph, nonlinearity=act)
+    m.prepare(w.X, idx, w.dev_indices, w.test_indices, w.Y, w.A_hat)
+    return m
+
+
+CASES = [(2, False, "rectify", False), (2, False, "rectify", True), (3, True, "rectify", False),
+         (4, True, "tanh", True), (3, False, "rectify", False)]
+
+
+@pytest.mark.parametrize("n_layers,highway,act,dup", CASES)
+def test_one_training_step_matches_oracle(n_layers, highway, act, dup):
+    w = workload()
+    rng = np.random.RandomState(5)
+    idx = w.train_indices
+    if dup:
+        idx = rng.choice(w.train_indices, size=len(w.train_indices)).astype(np.int32)     # tensormain.py:226
+    params = go.init_params(rng, w.X.shape[1], w.hidden, w.n_classes, n_layers, highway)
+    for p in params:
+        if p.ndim == 1:
+            p[...] = (rng.standard_normal(p.shape) * 0.05).astype(np.float32)
+    reg = (1e-4, 2e-4)
+    net = go.GCNOracle(w.X, w.A_hat, n_layers, highway, reg, act)
+    y = w.Y[idx].astype(np.int32)
+    loss, acc, grads, cache = net.loss_and_grads(params, idx, y)
+    m = make_model(w, n_layers, highway, params, idx, act=act, reg=reg)
+    m.f_train()
+    torch.cuda.synchronize()
+    l_gpu, a_gpu = m.train_results()
+    assert abs(l_gpu - float(loss)) <= 1e-6 + 1e-5 * abs(float(loss))
+    assert abs(a_gpu - acc) < 1e-6
+    # per-layer activations
+    convs = [ly for ly in m.layers]
+    for i, ly in enumerate(convs[:-1]):
+        assert_close(ly._out.cpu().numpy(), cache["A"][i], what="activation of layer %d" % (i + 1))
+    assert_close(m.l_out._out.cpu().numpy(), cache["logits"], atol=2e-6, what="logits")
+    # per-parameter gradients (the reg sub-gradient is folded into the GPU Adam kernel, so add it here)
+    gpu_grads = m.get_grad_values()
+    k = 0
+    for li, ly in enumerate(m.layers):
+        for name, t, tags in ly.params:
+            g = gpu_grads[k]
+            if tags.get("regularizable"):
+                c = np.float32(reg[0] if ly is m.l_out else reg[1])
+                g = g + np.float32(0.5) * c * (np.sign(params[k]) + np.float32(2) * params[k])
+            assert_close(g, grads[k], what="grad of layer %d %s" % (li + 1, name))
+            k += 1
+    # parameters after the Adam step
+    st = go.AdamState(params)
+    go.adam_step(params, grads, st)
+    for p_gpu, p in zip(m.get_param_values(), params):
+        assert_close(p_gpu, p, atol=2e-6, what="params after step")
+
+
+@pytest.mark.parametrize("n_layers,highway", [(2, False), (3, True)])
+def test_five_step_trajectory_and_predictions(n_layers, highway):
+    w = workload()
+    rng = np.random.RandomState(11)
+    params = go.init_params(rng, w.X.shape[1], w.hidden, w.n_classes, n_layers, highway)
+    idx = w.train_indices
+    y = w.Y[idx].astype(np.int32)
+    net = go.GCNOracle(w.X, w.A_hat, n_layers, highway, (1e-4, 2e-4))
+    ref_params = [p.copy() for p in params]
+    hist = go.train_epochs(net, ref_params, idx, y, 5)
+    m = make_model(w, n_layers, highway, params, idx, cuda_graph=True)     # epochs 2..5 replay the graph
+    for step in range(5):
+        m.f_train()
+        l, a = m.train_results()
+        assert abs(l - hist[step][0]) <= 2e-5 * abs(hist[step][0]), (step, l, hist[step])
+        assert abs(a - hist[step][1]) <= 2.0 / len(idx)
+    assert m._graph is not None
+    for p_gpu, p in zip(m.get_param_values(), ref_params):
+        assert_close(p_gpu, p, atol=1e-5, rtol=1e-3, what="params after 5 steps")
+    # predictions with identical parameters: argmax identical except exact logit ties
+    from graphconvgeo_b200 import lasagne_layers as L
+    L.set_all_param_values(m.l_out, ref_params)
+    for part, pidx in (("dev", w.dev_indices), ("test", w.test_indices), ("train", idx)):
+        proba = m.predict_proba(part)
+        ref = net.predict_proba(ref_params, pidx)
+        assert_close(proba, ref, atol=1e-6, what="predict_proba " + part)
+        pred = m.predict(part)
+        assert pred.dtype == np.int64
+        top2 = np.sort(ref, axis=1)[:, -2:]
+        tie = (top2[:, 1] - top2[:, 0]) <= 1e-6
+        assert np.array_equal(pred[~tie], ref.argmax(-1)[~tie])
+    acc = m.accuracy("test", w.Y[w.test_indices].astype(np.int32))
+    _, ref_acc = net.loss_acc(ref_params, w.test_indices, w.Y[w.test_indices].astype(np.int32))
+    assert abs(acc - ref_acc) <= 2.0 / len(w.test_indices)
+
+
+def test_cuda_graph_replay_equals_eager():
+    w = workload()
+    rng = np.random.RandomState(3)
+    params = go.init_params(rng, w.X.shape[1], w.hidden, w.n_classes, 3, True)
+    a = make_model(w, 3, True, params, w.train_indices, cuda_graph=True)
+    b = make_model(w, 3, True, params, w.train_indices, cuda_graph=False)
+    for _ in range(4):
+        a.f_train()
+        b.f_train()
+    torch.cuda.synchronize()
+    for pa, pb in zip(a.get_param_values(), b.get_param_values()):
+        assert np.array_equal(pa, pb)            # same kernels, same order -> same bits
+    assert a.train_results() == b.train_results()
+
+
+def test_fit_learns_and_keeps_the_reference_interface(tmp_path):
+    from graphconvgeo_b200.mlpconv import MLPCONV
+    w = workload()
+    clf = MLPCONV(n_epochs=61, batch_size=500, init_parameters=None, complete_prob=False, add_hidden=True,
+                  regul_coefs=[1e-6, 1e-6], save_results=False, hidden_layer_size=w.hidden, drop_out=False,
+                  dropout_coefs=[0.5, 0.5], early_stopping_max_down=5, loss_name='log', nonlinearity='rectify',
+                  dtype='float32', seed=1, model_dir=str(tmp_path))
+    clf.fit(w.X, w.train_indices, w.dev_indices, w.test_indices, w.Y, w.A_hat)       # tensormain.py:237
+    acc = clf.accuracy(dataset_partition='test', y_true=w.Y[w.test_indices].astype('int32'))
+    y_pred = clf.predict(dataset_partition='test')
+    assert y_pred.shape == (len(w.test_indices),)
+    assert acc > 3.0 / w.n_classes, acc          # far above chance: labels follow the graph communities
+    assert abs(acc - np.mean(y_pred == w.Y[w.test_indices])) < 1e-6
+    files = list(tmp_path.iterdir())
+    assert len(files) == 1 and files[0].name.startswith("Xshape1_%d_hidden_%d" % (w.X.shape[1], w.hidden))
+    import pickle
+    best = pickle.load(open(files[0], "rb"))
+    assert [b.shape for b in best] == [p.shape for p in clf.get_param_values()]
+    with pytest.raises(ValueError):
+        clf.predict("validation")
+
+
+def test_geotext_shape_reference_network_step():
+    """BASELINE config 1/2 shape (GEOTEXT: 9,475 users, 9k vocab, 128 regions, hid 300)."""
+    w = workload("geotext")
+    rng = np.random.RandomState(0)
+    for n_layers, highway in ((2, False), (3, True)):
+        params = go.init_params(rng, w.X.shape[1], w.hidden, w.n_classes, n_layers, highway)
+        net = go.GCNOracle(w.X, w.A_hat, n_layers, highway, (1e-6, 1e-6))
+        y = w.Y[w.train_indices].astype(np.int32)
+        loss, acc, grads, cache = net.loss_and_grads(params, w.train_indices, y)
+        m = make_model(w, n_layers, highway, params, w.train_indices, reg=(1e-6, 1e-6))
+        m.f_train()
+        l_gpu, a_gpu = m.train_results()
+        assert abs(l_gpu - float(loss)) <= 1e-5 * abs(float(loss))
+        for i, ly in enumerate(m.layers[:-1]):
+            assert_close(ly._out.cpu().numpy(), cache["A"][i], what="activation %d" % i)
+        gpu_grads = m.get_grad_values()
+        k = 0
+        for ly in m.layers:
+            for name, t, tags in ly.params:
+                g = gpu_grads[k]
+                if tags.get("regularizable"):
+                    g = g + np.float32(0.5e-6) * (np.sign(params[k]) + np.float32(2) * params[k])
+                assert_close(g, grads[k], what="grad %d" % k)
+                k += 1
