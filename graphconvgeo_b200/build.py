@@ -24,7 +24,7 @@ SOURCES = ["gcg_core.cu", "gcg_spmm.cu", "gcg_gemm.cu", "gcg_gemm_tc.cu", "gcg_e
            "gcg_host.cpp", "gcg_peer.cu"]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC,-O3,-Wall", "--expt-relaxed-constexpr",
+              "-Xcompiler", "-fPIC,-O3,-Wall,-fopenmp", "--expt-relaxed-constexpr",
               "-I", INCLUDE, "-I", CSRC]
 
 
@@ -72,7 +72,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     with cf.ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
         objs = list(ex.map(compile_one, srcs))
-    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + ["-Xcompiler", "-fopenmp"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))

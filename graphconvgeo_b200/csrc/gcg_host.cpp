@@ -193,3 +193,37 @@ extern "C" int64_t gcg_csr_gather_rows_host(int64_t n_rows, const int32_t* indpt
   }
   return nnz;
 }
+
+extern "C" int gcg_csr_permute_host(int64_t n_rows, const int32_t* indptr, const int32_t* indices,
+                                    const float* vals, const int32_t* order, const int32_t* col_map,
+                                    int32_t* out_indptr, int32_t* out_indices, float* out_vals) {
+  GCG_CHECK_ARG(indptr && order && out_indptr && (indptr[n_rows] == 0 || (indices && vals && out_indices && out_vals)),
+                "gcg_csr_permute_host: NULL argument");
+  out_indptr[0] = 0;
+  for (int64_t i = 0; i < n_rows; ++i) {
+    const int64_t r = order[i];
+    if (r < 0 || r >= n_rows) { set_error("gcg_csr_permute_host: order[%lld] out of range", (long long)i); return GCG_ERR_SHAPE; }
+    out_indptr[i + 1] = out_indptr[i] + (indptr[r + 1] - indptr[r]);
+  }
+#pragma omp parallel
+  {
+    std::vector<std::pair<int32_t, float>> tmp;
+#pragma omp for schedule(dynamic, 1024)
+    for (int64_t i = 0; i < n_rows; ++i) {
+      const int64_t r = order[i];
+      const int32_t b = indptr[r], len = indptr[r + 1] - b;
+      int32_t* oi = out_indices + out_indptr[i];
+      float* ov = out_vals + out_indptr[i];
+      if (!col_map) {
+        std::memcpy(oi, indices + b, sizeof(int32_t) * len);
+        std::memcpy(ov, vals + b, sizeof(float) * len);
+        continue;
+      }
+      tmp.resize(len);
+      for (int32_t k = 0; k < len; ++k) tmp[k] = {col_map[indices[b + k]], vals[b + k]};
+      std::sort(tmp.begin(), tmp.end(), [](const std::pair<int32_t, float>& x, const std::pair<int32_t, float>& y) { return x.first < y.first; });
+      for (int32_t k = 0; k < len; ++k) { oi[k] = tmp[k].first; ov[k] = tmp[k].second; }
+    }
+  }
+  return GCG_OK;
+}

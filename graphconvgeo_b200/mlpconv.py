@@ -51,7 +51,8 @@ class MLPCONV:
                  seed=None,
                  cuda_graph=True,
                  model_dir=None,
-                 learning_rate=4e-3):
+                 learning_rate=4e-3,
+                 reorder="auto"):
         # mlpconv.py:136-150
         self.n_epochs = n_epochs
         self.batch_size = batch_size          # accepted and ignored: full batch (mlpconv.py:294)
@@ -75,6 +76,7 @@ class MLPCONV:
         self.cuda_graph = cuda_graph
         self.model_dir = model_dir
         self.learning_rate = learning_rate
+        self.reorder = reorder      # None | "auto" | "labels" | "degree" | explicit permutation (new -> old)
         if complete_prob:
             raise NotImplementedError("complete_prob=True (dense label distributions) is unused by the "
                                       "reference driver (tensormain.py:232) and not on the hot path")
@@ -250,11 +252,34 @@ class MLPCONV:
                     in_size, self.hidden_layer_size, out_size, str(self.dropout_coefs), str(self.regul_coefs), self.dtype)
         self.Xd = as_csr(X, self.device, long_row_threshold=1024)
         Hd = as_csr(H, self.device)
+        # node reordering (performance only; the net is permutation equivariant): nodes of the same
+        # region become neighbours in memory, so gathered rows of A_hat.H share L2 lines
+        n_nodes = Hd.shape[0]
+        mode = self.reorder
+        if isinstance(mode, str) and mode == "auto":
+            mode = "labels" if n_nodes >= 100000 else None
+        self.node_order = None                       # new position -> original node id
+        node_map = lambda idx: np.asarray(idx)
+        if mode is not None:
+            if isinstance(mode, str) and mode == "labels":
+                order = np.argsort(Y[:n_nodes], kind="stable").astype(np.int32)
+            elif isinstance(mode, str) and mode == "degree":
+                deg = np.diff(Hd._host_arrays()[0])
+                order = np.argsort(-deg, kind="stable").astype(np.int32)
+            else:
+                order = np.ascontiguousarray(np.asarray(mode), dtype=np.int32)
+            inv = np.empty(n_nodes, np.int32)
+            inv[order] = np.arange(n_nodes, dtype=np.int32)
+            self.Xd = self.Xd.permute(order)
+            Hd = Hd.permute(order, col_map=inv)
+            self.node_order, self.node_inverse = order, inv
+            node_map = lambda idx: inv[np.asarray(idx)]
+        self._node_map = node_map
         self._build(self.Xd, Hd, in_size, out_size)
         Hd = self.l_hid1.H
-        self.ti = {"train": L.TargetIndices(train_indices, Hd),
-                   "dev": L.TargetIndices(dev_indices, Hd),
-                   "test": L.TargetIndices(test_indices, Hd)}
+        self.ti = {"train": L.TargetIndices(node_map(train_indices), Hd),
+                   "dev": L.TargetIndices(node_map(dev_indices), Hd),
+                   "test": L.TargetIndices(node_map(test_indices), Hd)}
         self.ti_train = self.ti["train"]
         to_dev = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).to(self.device)
         self.y_train_dev = to_dev(Y_train)                                 # :276-277 int32
@@ -331,8 +356,13 @@ class MLPCONV:
     def get_embedding(self, indices):
         """Hidden representation of ``indices`` (a stub in the reference, mlpconv.py:350-352)."""
         self._forward(self.ti["dev"], train=False)
-        idx = torch.from_numpy(np.ascontiguousarray(indices, dtype=np.int32)).to(self.device)
+        idx = torch.from_numpy(np.ascontiguousarray(self._node_map(indices), dtype=np.int32)).to(self.device)
         return ops.gather_rows(self.layers[-2]._out, idx).cpu().numpy()
+
+    def node_rows(self, t):
+        """A per-node device matrix (e.g. a layer's ``_out``) as a host array in ORIGINAL node order."""
+        a = t.detach().cpu().numpy()
+        return a if self.node_order is None else a[self.node_inverse]
 
     def get_param_values(self):
         return L.get_all_param_values(self.l_out)

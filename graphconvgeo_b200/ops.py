@@ -17,7 +17,10 @@ from .sparse import CSRMatrix
 
 # L2 budget used to pick the SpMM column-panel width: one panel of the gathered
 # operand (n_cols * panel * 4 bytes) should stay resident in the 126 MB L2.
-L2_PANEL_BUDGET_BYTES = int(os.environ.get("GCG_L2_PANEL_BUDGET", 64 << 20))
+# Measured on B200 (profiles/r01_spmm_twitter_us.md): a 57.6 MB panel only reaches a 43% L2 hit
+# rate (the two L2 partitions replicate lines read from both dies) and the re-read CSR arrays cost
+# more than the hits save, so panel mode is OFF by default (budget 0) and selected explicitly.
+L2_PANEL_BUDGET_BYTES = int(os.environ.get("GCG_L2_PANEL_BUDGET", 0))
 _FORCE_PANEL = os.environ.get("GCG_SPMM_PANEL")          # experiments: force panel_cols
 _GEMM_MODE = os.environ.get("GCG_GEMM_MODE", "auto")     # "fma" | "tf32x3" | "tf32" | "auto"
 
@@ -88,7 +91,7 @@ scratch = _Scratch()
 def auto_panel_cols(n_cols, F):
     if _FORCE_PANEL is not None:
         return int(_FORCE_PANEL)
-    if n_cols * F * 4 <= L2_PANEL_BUDGET_BYTES:
+    if L2_PANEL_BUDGET_BYTES <= 0 or n_cols * F * 4 <= L2_PANEL_BUDGET_BYTES:
         return 0
     p = 16
     while p * 2 < F and n_cols * (p * 2) * 4 <= L2_PANEL_BUDGET_BYTES:

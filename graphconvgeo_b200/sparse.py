@@ -157,6 +157,23 @@ class CSRMatrix:
                                    self.long_row_threshold)
 
 
+    def permute(self, order, col_map=None):
+        """P A Q^T: row i of the result is row order[i]; column j becomes col_map[j]
+        (None keeps the columns).  One-off host operation (gcg_csr_permute_host)."""
+        order = np.ascontiguousarray(np.asarray(order), dtype=np.int32)
+        cm = None if col_map is None else np.ascontiguousarray(np.asarray(col_map), dtype=np.int32)
+        ip, ix, d = self._host_arrays()
+        n = self.shape[0]
+        assert len(order) == n
+        oip = np.empty(n + 1, np.int32)
+        oix = np.empty(len(ix), np.int32)
+        od = np.empty(len(ix), np.float32)
+        _lib.check(_lib.lib().gcg_csr_permute_host(n, _np_ptr(ip), _np_ptr(ix), _np_ptr(d), _np_ptr(order),
+                                                   _np_ptr(cm) if cm is not None else None, _np_ptr(oip),
+                                                   _np_ptr(oix), _np_ptr(od)), "gcg_csr_permute_host")
+        return CSRMatrix.from_host((oip, oix, od), self.shape, self.device, self.long_row_threshold)
+
+
 def as_csr(x, device="cuda", long_row_threshold=256) -> CSRMatrix:
     if isinstance(x, CSRMatrix):
         return x

@@ -241,6 +241,16 @@ int64_t gcg_csr_gather_rows_host(int64_t n_rows, const int32_t* h_indptr,
                                  const int32_t* idx, int64_t n_idx, int32_t* out_indptr,
                                  int32_t* out_indices, float* out_vals);
 
+/* Node reordering for gather locality: out = P A Q^T where row i of out is row
+ * order[i] of A and column j of A becomes col_map[j] (col_map == NULL keeps the
+ * columns); columns are re-sorted inside every row.  The GCN is permutation
+ * equivariant, so running it on (P A_hat P^T, P X) and mapping target_indices
+ * through P changes no result of lasagne_layers.py:60-89, only which dense rows
+ * sit next to each other in HBM / L2.  Output arrays have the input's nnz. */
+int gcg_csr_permute_host(int64_t n_rows, const int32_t* h_indptr, const int32_t* h_indices,
+                         const float* h_vals, const int32_t* order, const int32_t* col_map,
+                         int32_t* out_indptr, int32_t* out_indices, float* out_vals);
+
 #ifdef __cplusplus
 }
 #endif

@@ -16,11 +16,11 @@ def workload(name="tiny", **kw):
     return synth.make_workload(name, **kw)
 
 
-def make_model(w, n_layers, highway, params, idx, cuda_graph=False, act="rectify", reg=(1e-4, 2e-4)):
+def make_model(w, n_layers, highway, params, idx, cuda_graph=False, act="rectify", reg=(1e-4, 2e-4), reorder=None):
     from graphconvgeo_b200.mlpconv import MLPCONV
     m = MLPCONV(n_epochs=1, regul_coefs=list(reg), hidden_layer_size=w.hidden, drop_out=False,
                 n_layers=n_layers, highway=highway, init_parameters=[p.copy() for p in params],
-                cuda_graph=cuda_graph, nonlinearity=act)
+                cuda_graph=cuda_graph, nonlinearity=act, reorder=reorder)
     m.prepare(w.X, idx, w.dev_indices, w.test_indices, w.Y, w.A_hat)
     return m
 
@@ -53,7 +53,7 @@ def test_one_training_step_matches_oracle(n_layers, highway, act, dup):
     # per-layer activations
     convs = [ly for ly in m.layers]
     for i, ly in enumerate(convs[:-1]):
-        assert_close(ly._out.cpu().numpy(), cache["A"][i], what="activation of layer %d" % (i + 1))
+        assert_close(m.node_rows(ly._out), cache["A"][i], what="activation of layer %d" % (i + 1))
     assert_close(m.l_out._out.cpu().numpy(), cache["logits"], atol=2e-6, what="logits")
     # per-parameter gradients (the reg sub-gradient is folded into the GPU Adam kernel, so add it here)
     gpu_grads = m.get_grad_values()
@@ -155,12 +155,13 @@ def test_geotext_shape_reference_network_step():
         net = go.GCNOracle(w.X, w.A_hat, n_layers, highway, (1e-6, 1e-6))
         y = w.Y[w.train_indices].astype(np.int32)
         loss, acc, grads, cache = net.loss_and_grads(params, w.train_indices, y)
-        m = make_model(w, n_layers, highway, params, w.train_indices, reg=(1e-6, 1e-6))
+        m = make_model(w, n_layers, highway, params, w.train_indices, reg=(1e-6, 1e-6),
+                       reorder="labels" if highway else None)
         m.f_train()
         l_gpu, a_gpu = m.train_results()
         assert abs(l_gpu - float(loss)) <= 1e-5 * abs(float(loss))
         for i, ly in enumerate(m.layers[:-1]):
-            assert_close(ly._out.cpu().numpy(), cache["A"][i], what="activation %d" % i)
+            assert_close(m.node_rows(ly._out), cache["A"][i], what="activation %d" % i)
         gpu_grads = m.get_grad_values()
         k = 0
         for ly in m.layers:
@@ -170,3 +171,33 @@ def test_geotext_shape_reference_network_step():
                     g = g + np.float32(0.5e-6) * (np.sign(params[k]) + np.float32(2) * params[k])
                 assert_close(g, grads[k], what="grad %d" % k)
                 k += 1
+
+
+@pytest.mark.parametrize("mode", ["labels", "degree", "random"])
+def test_node_reordering_changes_no_result(mode):
+    """The GCN is permutation equivariant: running on (P A P^T, P X) with mapped target indices gives
+    the same loss, gradients, activations (in original order) and predictions."""
+    w = workload()
+    rng = np.random.RandomState(21)
+    params = go.init_params(rng, w.X.shape[1], w.hidden, w.n_classes, 3, True)
+    idx = rng.choice(w.train_indices, size=500).astype(np.int32)
+    y = w.Y[idx].astype(np.int32)
+    net = go.GCNOracle(w.X, w.A_hat, 3, True, (1e-4, 2e-4))
+    loss, acc, grads, cache = net.loss_and_grads(params, idx, y)
+    reorder = rng.permutation(w.X.shape[0]).astype(np.int32) if mode == "random" else mode
+    m = make_model(w, 3, True, params, idx, reorder=reorder)
+    assert m.node_order is not None
+    m.f_train()
+    l_gpu, a_gpu = m.train_results()
+    assert abs(l_gpu - float(loss)) <= 1e-5 * abs(float(loss)) and abs(a_gpu - acc) < 1e-6
+    for i, ly in enumerate(m.layers[:-1]):
+        assert_close(m.node_rows(ly._out), cache["A"][i], what="activation %d" % i)
+    assert_close(m.l_out._out.cpu().numpy(), cache["logits"], atol=2e-6)      # idx order is untouched
+    st = go.AdamState(params)
+    go.adam_step(params, grads, st)
+    for p_gpu, p in zip(m.get_param_values(), params):
+        assert_close(p_gpu, p, atol=2e-6)
+    ref = net.predict_proba(params, w.test_indices)
+    assert_close(m.predict_proba("test"), ref, atol=1e-6)
+    emb = m.get_embedding(w.dev_indices[:7])
+    assert emb.shape == (7, w.hidden)
