@@ -171,7 +171,8 @@ def run_gpu(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
 
     t0 = time.time()
     wl = synth.make_workload_device(args.workload, device=dev, seed=77, community=not args.random_graph)
@@ -240,7 +241,7 @@ def run_gpu(args):
         e2e = measure_e2e(m, args, dev, flush)
 
     # ---------------- roofline of the headline kernel: A_hat . H  (F = hidden)
-    roof = spmm_roofline(m, wl, dev) if rank == 0 else None
+    roof = spmm_roofline(m, wl, dev)          # collective in row-partitioned mode: every rank calls it
 
     if rank != 0:
         if world > 1:
@@ -315,12 +316,15 @@ def spmm_roofline(m, wl, dev, reps=10):
     peak, peak_src = measured_peaks()
     A = m.l_hid1.H
     H = m.l_hid1._out
-    N, F = H.shape
+    N, F = H.shape                      # local rows in row-partitioned mode
     out = ops.alloc_mat(N, F, dev)
     nnz = A.nnz
-    alg_bytes = 8 * nnz + 4 * (N + 1) + 8 * N * F
+    n_in = A.shape[1]
+    # compulsory traffic of this rank's launch(es): CSR once, the gathered operand once, the output once
+    alg_bytes = 8 * nnz + 4 * (N + 1) + 4 * n_in * F + 4 * N * F
     results = {}
-    for label, panel in (("auto", None), ("rows", 0)):
+    dist_mode = hasattr(A, "dist_spmm")
+    for label, panel in ((("auto", None),) if dist_mode else (("auto", None), ("rows", 0))):
         for _ in range(3):
             ops.spmm(A, H, out=out, panel_cols=panel)
         ts = []
@@ -336,12 +340,13 @@ def spmm_roofline(m, wl, dev, reps=10):
     achieved = alg_bytes / (t_ms * 1e-3) / 1e9
     gather_model = (8 * nnz + 4 * nnz * F + 4 * N * F) / (t_ms * 1e-3) / 1e9
     return {"roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "spmm_vec_kernel (A_hat.H, F=%d)" % F,
+                         "traffic": None, "kernel": "spmm_vec_kernel (A_hat.H, F=%d%s)" % (F, ", local rows incl. NCCL all-gather of H" if dist_mode else ""),
                          "algorithmic_bytes": alg_bytes, "ms": t_ms, "peak_source": peak_src,
                          "frac_of_nominal_8000": achieved / 8000.0},
-            "detail": {"N": N, "F": F, "nnz": nnz, "ms_auto_panel": results["auto"], "ms_whole_rows": results["rows"],
+            "detail": {"N": N, "F": F, "nnz": nnz, "ms_auto_panel": results["auto"], "ms_whole_rows": results.get("rows"),
                        "panel_cols_auto": ops.auto_panel_cols(N, F), "gather_model_GBps": gather_model,
-                       "plan": A.plan_info()}}
+                       "plan": None if dist_mode else A.plan_info(),
+                       "diag_fraction": getattr(A, "diag_fraction", None)}}
 
 
 def main():

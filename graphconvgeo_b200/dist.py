@@ -1,0 +1,348 @@
+"""Row-partitioned multi-GPU execution of the GCN hot path (one process per GPU).
+
+The reference is single-process; this is the scaling design BASELINE.json's
+north_star asks for:
+  * rank p owns the contiguous node range [p*n_loc, (p+1)*n_loc) of A_hat (all columns), of X,
+    of every activation / gradient slab and of the target indices falling in its range;
+    parameters and Adam state are replicated.
+  * every propagation A_hat.Z needs all rows of the dense operand: the local slab lives inside a
+    full [P*n_loc, F] buffer and is all-gathered IN PLACE with NCCL over NVLink (asynchronously,
+    on NCCL's stream) while the main stream already runs the SpMM over the DIAGONAL column block
+    (local columns only read the local slab); the off-diagonal block follows with
+    accumulate + the fused epilogue once the gather has landed.
+  * parameter gradients are partial sums over local rows -> all-reduce (async, overlapped with
+    the rest of the backward); loss / accuracy partial sums -> one small all-reduce.
+  * X.W1, all dense GEMMs, epilogues, the gate and Adam need no communication.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import lasagne_layers as L
+from . import ops
+from .mlpconv import MLPCONV
+from .sparse import CSRMatrix, as_csr
+
+
+class RowPartition:
+    """Equal contiguous row blocks (padded): n_loc = ceil(N / P) rounded up to 4 rows."""
+
+    def __init__(self, n_total, world, rank, device=None, group=None):
+        self.n_total, self.world, self.rank = int(n_total), int(world), int(rank)
+        self.n_loc = (-(-self.n_total // self.world) + 3) // 4 * 4
+        self.n_pad = self.n_loc * self.world
+        self.r0 = min(self.n_total, self.rank * self.n_loc)
+        self.r1 = min(self.n_total, self.r0 + self.n_loc)
+        self.device = device
+        self.group = group
+        self._full = {}
+        self.bytes_gathered = 0
+
+    def owner(self, rows):
+        return np.asarray(rows) // self.n_loc
+
+    def local_rows(self, rows):
+        """positions (into ``rows``) owned by this rank, and their local row ids"""
+        rows = np.asarray(rows, dtype=np.int64)
+        sel = np.flatnonzero((rows >= self.r0) & (rows < self.r1))
+        return sel, (rows[sel] - self.rank * self.n_loc).astype(np.int32)
+
+    # full [n_pad, F] operand buffers, one per (key, F); the local slab is a view into it
+    def full(self, key, F):
+        k = (key, int(F))
+        buf = self._full.get(k)
+        if buf is None:
+            buf = ops.alloc_mat(self.n_pad, F, self.device, zero=True)
+            self._full[k] = buf
+        return buf
+
+    def local_view(self, full):
+        return full[self.rank * self.n_loc:(self.rank + 1) * self.n_loc]
+
+    def all_gather_async(self, full):
+        """in-place NCCL all-gather of the slabs of ``full``; returns the Work handle."""
+        base = full._base if full._base is not None else full
+        flat = base.view(-1)
+        per = flat.numel() // self.world
+        self.bytes_gathered += (self.world - 1) * per * 4
+        return dist.all_gather_into_tensor(flat, flat[self.rank * per:(self.rank + 1) * per],
+                                           group=self.group, async_op=True)
+
+
+def split_columns(host, c0, c1):
+    """(indptr, indices, vals) -> (diag part with columns in [c0, c1), the rest); order preserved."""
+    ip, ix, d = host
+    n = len(ip) - 1
+    rows = np.repeat(np.arange(n, dtype=np.int64), np.diff(ip))
+    m = (ix >= c0) & (ix < c1)
+
+    def take(mask):
+        cnt = np.bincount(rows[mask], minlength=n)
+        p = np.zeros(n + 1, np.int32)
+        np.cumsum(cnt, out=p[1:])
+        return (p, np.ascontiguousarray(ix[mask]), np.ascontiguousarray(d[mask]))
+
+    return take(m), take(~m)
+
+
+class DistCSRMatrix:
+    """Rows owned by this rank of a row-partitioned sparse matrix whose dense operand is
+    row-partitioned too.  ``spmm`` = async all-gather of the operand overlapped with the
+    diagonal-block SpMM, then the off-diagonal block with accumulate + epilogue."""
+
+    def __init__(self, part: RowPartition, host, n_rows, long_row_threshold=256):
+        self.part = part
+        self.host = host
+        self.shape = (int(n_rows), part.n_pad)
+        self.long_row_threshold = long_row_threshold
+        c0 = part.rank * part.n_loc
+        dg, off = split_columns(host, c0, c0 + part.n_loc)
+        self.diag = CSRMatrix.from_host(dg, self.shape, part.device, long_row_threshold)
+        self.off = CSRMatrix.from_host(off, self.shape, part.device, long_row_threshold)
+        self.nnz = len(host[1])
+        self.diag_fraction = (len(dg[1]) / max(1, self.nnz))
+
+    @property
+    def device(self):
+        return self.part.device
+
+    @classmethod
+    def from_global(cls, A: CSRMatrix, part: RowPartition):
+        ip, ix, d = A._host_arrays()
+        lo, hi = part.r0, part.r1
+        p = np.zeros(part.n_loc + 1, np.int32)
+        p[:hi - lo + 1] = ip[lo:hi + 1] - ip[lo]
+        p[hi - lo + 1:] = p[hi - lo]
+        host = (p, np.ascontiguousarray(ix[ip[lo]:ip[hi]]), np.ascontiguousarray(d[ip[lo]:ip[hi]]))
+        return cls(part, host, part.n_loc, A.long_row_threshold)
+
+    def gather_rows(self, local_idx):
+        local_idx = np.asarray(local_idx, dtype=np.int64)
+        ip, ix, d = self.host
+        lens = (ip[local_idx + 1] - ip[local_idx]).astype(np.int64)
+        p = np.zeros(len(local_idx) + 1, np.int32)
+        np.cumsum(lens, out=p[1:])
+        starts = ip[local_idx].astype(np.int64)
+        take = np.repeat(starts - p[:-1].astype(np.int64), lens) + np.arange(int(p[-1]), dtype=np.int64)
+        host = (p, np.ascontiguousarray(ix[take]), np.ascontiguousarray(d[take]))
+        return DistCSRMatrix(self.part, host, len(local_idx), self.long_row_threshold)
+
+    def operand(self, key, F):
+        """local slab [n_loc, F] that lives inside the full gather buffer (no staging copy)."""
+        return self.part.local_view(self.part.full(key, F))
+
+    def dist_spmm(self, B, out=None, key="stage", **epi):
+        part = self.part
+        F = B.shape[1]
+        full = None
+        for (k, f), buf in part._full.items():           # is B already a slab of a gather buffer?
+            if f == F and part.local_view(buf).data_ptr() == B.data_ptr():
+                full = buf
+                break
+        if full is None:
+            full = part.full(key, F)
+            part.local_view(full).copy_(B)
+        work = part.all_gather_async(full)                # NCCL stream; waits for what is enqueued so far
+        if out is None:
+            out = ops.alloc_mat(self.shape[0], F, B.device)
+        if self.shape[0] > 0:
+            ops.spmm(self.diag, full, out=out)            # local columns: only the local slab is read
+        work.wait()                                       # main stream waits for the gather
+        if self.shape[0] == 0:
+            return out
+        return ops.spmm(self.off, full, out=out, accumulate=True, **epi)
+
+
+class DistTargetIndices(L.TargetIndices):
+    """The part of a target_indices vector whose nodes this rank owns."""
+
+    def __init__(self, idx_global_perm, H: DistCSRMatrix, n_global):   # noqa: super().__init__ not wanted
+        part = H.part
+        self.sel, self.local = part.local_rows(idx_global_perm)
+        self.n = len(self.local)
+        self.n_global = int(n_global)
+        self.device = part.device
+        self.H = H
+        self.dev = torch.from_numpy(self.local).to(self.device)
+        self._Hsub = None
+        self._pos = None
+
+    @property
+    def Hsub(self):
+        if self._Hsub is None:
+            self._Hsub = self.H.gather_rows(self.local)
+        return self._Hsub
+
+    @property
+    def positions(self):
+        if self._pos is None:
+            self._pos = ops.scatter_positions(self.local, self.H.shape[0], self.device)
+        return self._pos
+
+
+class DistMLPCONV(MLPCONV):
+    """MLPCONV over a row-partitioned graph.  Every rank is given the same full inputs (as the
+    single-process fit() is); each keeps its row block.  Results (loss, acc, predictions gathered
+    over ranks, parameters) equal the single-GPU ones up to summation order of the all-reduces."""
+
+    def __init__(self, *args, group=None, **kwargs):
+        kwargs["cuda_graph"] = False          # NCCL work is enqueued eagerly
+        super().__init__(*args, **kwargs)
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+
+    def prepare(self, X, train_indices, dev_indices, test_indices, Y, H):
+        Y = np.asarray(Y)
+        in_size = X.shape[1]
+        out_size = int(np.max(Y)) + 1
+        self.X, self.H = X, H
+        self.train_indices, self.dev_indices, self.test_indices = train_indices, dev_indices, test_indices
+        Xg = as_csr(X, self.device, long_row_threshold=1024)
+        Hg = as_csr(H, self.device)
+        n = Hg.shape[0]
+        mode = self.reorder
+        if isinstance(mode, str) and mode == "auto":
+            mode = "labels"
+        self.node_order = None
+        inv = None
+        if mode is not None:
+            if isinstance(mode, str) and mode == "labels":
+                order = np.argsort(Y[:n], kind="stable").astype(np.int32)
+            elif isinstance(mode, str) and mode == "degree":
+                order = np.argsort(-np.diff(Hg._host_arrays()[0]), kind="stable").astype(np.int32)
+            else:
+                order = np.ascontiguousarray(np.asarray(mode), dtype=np.int32)
+            inv = np.empty(n, np.int32)
+            inv[order] = np.arange(n, dtype=np.int32)
+            Xg = Xg.permute(order)
+            Hg = Hg.permute(order, col_map=inv)
+            self.node_order, self.node_inverse = order, inv
+        node_map = (lambda i: np.asarray(i)) if inv is None else (lambda i: inv[np.asarray(i)])
+        self._node_map = node_map
+        part = RowPartition(n, self.world, self.rank, self.device, self.group)
+        self.part = part
+        Hd = DistCSRMatrix.from_global(Hg, part)
+        # local rows of X (padded with empty rows)
+        ip, ix, d = Xg._host_arrays()
+        p = np.zeros(part.n_loc + 1, np.int32)
+        p[:part.r1 - part.r0 + 1] = ip[part.r0:part.r1 + 1] - ip[part.r0]
+        p[part.r1 - part.r0 + 1:] = p[part.r1 - part.r0]
+        self.Xd = CSRMatrix.from_host((p, np.ascontiguousarray(ix[ip[part.r0]:ip[part.r1]]),
+                                       np.ascontiguousarray(d[ip[part.r0]:ip[part.r1]])),
+                                      (part.n_loc, in_size), self.device, 1024)
+        del Xg, Hg
+        self._build(self.Xd, Hd, in_size, out_size)
+        self.ti = {}
+        self._sel = {}
+        for name, idx in (("train", train_indices), ("dev", dev_indices), ("test", test_indices)):
+            t = DistTargetIndices(node_map(idx), Hd, len(idx))
+            self.ti[name] = t
+            self._sel[name] = t.sel
+        self.ti_train = self.ti["train"]
+        to_dev = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).to(self.device)
+        self.y_train_dev = to_dev(Y[np.asarray(train_indices)][self.ti["train"].sel])
+        self.y_dev_dev = to_dev(Y[np.asarray(dev_indices)][self.ti["dev"].sel])
+        self._heads = {}
+        self._graph = None
+        self._steps_done = 0
+        self._train_hb = None
+        self._red = torch.zeros(3, dtype=torch.float32, device=self.device)
+        return self
+
+    # ------------------------------------------------------------------ steps
+    def _head(self, logits, y, n_global, grad=None):
+        n, C = logits.shape
+        hb = self._head_buffers(max(n, 1), C)
+        if n > 0:
+            ops.softmax_ce(logits, y=y, grad=grad, ce=hb["ce"][:n], hit=hb["hit"][:n], denom=n_global)
+            ops.sum_scaled(hb["ce"][:n], 1.0 / n_global, out=hb["out"][0:1])
+            ops.sum_scaled(hb["hit"][:n], 1.0 / n_global, out=hb["out"][1:2])
+        else:
+            hb["out"].zero_()
+        return hb
+
+    def _train_step_enqueue(self):
+        ti, y = self.ti_train, self.y_train_dev
+        logits = self._forward(ti, train=True)
+        n, C = logits.shape
+        G = self.l_out._mat("G", n, C)
+        hb = self._head(logits, y, ti.n_global, grad=G)
+        self._backward(G)
+        works = [dist.all_reduce(g, group=self.group, async_op=True) for g in self.grads]
+        works.append(dist.all_reduce(hb["out"], group=self.group, async_op=True))
+        for w in works:
+            w.wait()
+        self.adam.step()
+        self._train_hb = hb
+
+    def _backward(self, G):
+        grad, preact = G, False
+        for i in range(len(self.layers) - 1, -1, -1):
+            ly = self.layers[i]
+            prev = self.layers[i - 1] if i > 0 else None
+            mask = None
+            if prev is not None and type(prev) in (L.SparseConvolutionDenseLayer, L.ConvolutionDenseLayer) \
+                    and prev.nonlinearity in ("rectify", "tanh"):
+                mask = (prev._out, prev.nonlinearity)
+            if isinstance(ly, L.SparseConvolutionDenseLayer):
+                ly.backward(grad, preact=preact)
+                break
+            if isinstance(ly, L.HighwayConvolutionDenseLayer):
+                grad = ly.backward(grad, input_mask=mask)
+            else:
+                grad = ly.backward(grad, preact=preact, input_mask=mask)
+            preact = mask is not None
+
+    def f_train(self):
+        self._train_step_enqueue()
+        self._steps_done += 1
+        return self._train_hb
+
+    def f_val(self, y, ti):
+        logits = self._forward(ti, train=False)
+        hb = self._head(logits, y, ti.n_global)
+        dist.all_reduce(hb["out"], group=self.group)
+        reg = self.elastic()
+        o = hb["out"].cpu().numpy()
+        return float(np.float32(o[0]) + np.float32(reg.item())), float(o[1])
+
+    def _gather_rows_to_all(self, local, ti, width, dtype):
+        """assemble per-target rows computed by their owners into the caller's index order"""
+        out = torch.zeros((ti.n_global, width), dtype=dtype, device=self.device)
+        if ti.n > 0:
+            out[torch.from_numpy(ti.sel).to(self.device)] = local.to(dtype).reshape(ti.n, width)
+        dist.all_reduce(out, group=self.group)
+        return out
+
+    def f_predict(self, ti):
+        logits = self._forward(ti, train=False)
+        n, C = logits.shape
+        hb = self._head_buffers(max(n, 1), C)
+        if n > 0:
+            ops.softmax_ce(logits, pred=hb["pred"][:n])
+        return self._gather_rows_to_all(hb["pred"][:n], ti, 1, torch.int64).cpu().numpy()[:, 0]
+
+    def f_predict_proba(self, ti):
+        logits = self._forward(ti, train=False)
+        n, C = logits.shape
+        probs = self.l_out._mat(("probs", n), max(n, 1), C)
+        if n > 0:
+            ops.softmax_ce(logits, probs=probs[:n])
+        return self._gather_rows_to_all(probs[:n].contiguous(), ti, C, torch.float32).cpu().numpy()
+
+    def accuracy(self, dataset_partition, y_true):
+        ti = self._partition(dataset_partition)
+        y = torch.from_numpy(np.ascontiguousarray(np.asarray(y_true)[ti.sel], dtype=np.int32)).to(self.device)
+        return self.f_val(y, ti)[1]
+
+    def node_rows(self, t):
+        """local slab -> full matrix in ORIGINAL node order (all-gathered; for tests)."""
+        part = self.part
+        full = torch.zeros((part.n_pad, t.shape[1]), dtype=t.dtype, device=self.device)
+        full[part.rank * part.n_loc:(part.rank + 1) * part.n_loc] = t
+        dist.all_reduce(full, group=self.group)
+        a = full[:part.n_total].cpu().numpy()
+        return a if self.node_order is None else a[self.node_inverse]

@@ -286,6 +286,13 @@ class _ConvBase(DenseLayer):
         self.H = None if H is None else as_csr(H, self.device)    # lasagne_layers.py:56,77 (not a param)
         self._ti_cache = {}
 
+    def _operand(self, key, n_rows, n_cols):
+        """buffer for a dense SpMM operand: in row-partitioned mode it is the local slab of the
+        (shared, transient) all-gather buffer, so no staging copy is needed"""
+        if hasattr(self.H, "operand"):
+            return self.H.operand(key, n_cols)
+        return self._mat(key, n_rows, n_cols)
+
     def _target(self, target_indices):
         if target_indices is None or isinstance(target_indices, TargetIndices):
             return target_indices
@@ -305,7 +312,7 @@ class SparseConvolutionDenseLayer(_ConvBase):
         X = as_csr(input, self.device)
         self._X = X
         N = X.shape[0]
-        z = ops.spmm(X, self.W, out=self._mat("Z", N, self.num_units))      # :65
+        z = ops.spmm(X, self.W, out=self._operand("Z", N, self.num_units))  # :65
         out = ops.spmm(self.H, z, bias=self.b, act=self.nonlinearity,
                        out=self._mat("out", N, self.num_units))             # :67-71 (bias+act fused)
         self._out = out
@@ -313,10 +320,10 @@ class SparseConvolutionDenseLayer(_ConvBase):
 
     def backward(self, grad_output, preact=False, **kwargs):
         dP = grad_output if preact or self.nonlinearity == "identity" else \
-            ops.act_bwd(grad_output, self._out, self.nonlinearity, out=self._mat("dP", *grad_output.shape))
+            ops.act_bwd(grad_output, self._out, self.nonlinearity, out=self._operand("dP", *grad_output.shape))
         if self.b is not None:
             ops.colsum(dP, out=self._grad("b", self.b))
-        dZ = ops.spmm(self.H, dP, out=self._mat("Z", *dP.shape))            # A_hat^T = A_hat; Z is dead: reuse
+        dZ = ops.spmm(self.H, dP, out=self._operand("Z", *dP.shape))        # A_hat^T = A_hat; Z is dead: reuse
         ops.spmm(self._X.T, dZ, out=self._grad("W", self.W))                # dW = X^T.dZ
         return None
 
@@ -335,7 +342,7 @@ class ConvolutionDenseLayer(_ConvBase):
         N = input.shape[0]
         self._in = input
         self._ti = ti
-        z = ops.gemm(input, self.W, out=self._mat("Z", N, self.num_units))   # :82
+        z = ops.gemm(input, self.W, out=self._operand("Z", N, self.num_units))   # :82
         Hm = self.H if ti is None else ti.Hsub
         n_out = N if ti is None else ti.n
         fused_act = "identity" if self.nonlinearity == "softmax" else self.nonlinearity
@@ -361,12 +368,12 @@ class ConvolutionDenseLayer(_ConvBase):
                               out=self._mat("dPr", *grad_output.shape))
         if ti is not None:
             ptr, pos = ti.positions
-            dP = ops.scatter_rows(dPr, ptr, pos, N, out=self._mat("dP", N, self.num_units))  # grad of :88
+            dP = ops.scatter_rows(dPr, ptr, pos, N, out=self._operand("dP", N, self.num_units))  # grad of :88
         else:
             dP = dPr
         if self.b is not None:
             ops.colsum(dP, out=self._grad("b", self.b))
-        dZ = ops.spmm(self.H, dP, out=self._mat("Z", N, self.num_units))     # A_hat^T.dP
+        dZ = ops.spmm(self.H, dP, out=self._operand("Z", N, self.num_units))     # A_hat^T.dP
         ops.gemm(self._in, dZ, transA=True, out=self._grad("W", self.W))     # dW = H_in^T.dZ
         if not need_input_grad:
             return None
@@ -395,7 +402,7 @@ class HighwayConvolutionDenseLayer(ConvolutionDenseLayer):
         assert kwargs.get("target_indices") is None, "a gated layer keeps all rows"
         N, h = input.shape[0], self.num_units
         self._in = input
-        z = ops.gemm(input, self.W, out=self._mat("Z", N, h))
+        z = ops.gemm(input, self.W, out=self._operand("Z", N, h))
         g = ops.gemm(input, self.Wg, bias=self.bg, act="sigmoid", out=self._mat("g", N, h))
         conv = self._mat("Hc", N, h) if kwargs.get("train", False) else None
         out = ops.spmm(self.H, z, bias=self.b, act=self.nonlinearity, gate=g, carry=input, conv_out=conv,
@@ -407,11 +414,11 @@ class HighwayConvolutionDenseLayer(ConvolutionDenseLayer):
         assert self._Hc is not None, "forward must run with train=True before backward"
         N, h = grad_output.shape
         dP, dG, dIn = ops.highway_bwd(grad_output, self._g, self._Hc, self._in, self.nonlinearity,
-                                      dP=self._mat("dP", N, h), dGpre=self._mat("dG", N, h),
+                                      dP=self._operand("dP", N, h), dGpre=self._mat("dG", N, h),
                                       dHin=self._mat("dIn", N, h))
         ops.colsum(dP, out=self._grad("b", self.b))
         ops.colsum(dG, out=self._grad("bg", self.bg))
-        dZ = ops.spmm(self.H, dP, out=self._mat("Z", N, h))
+        dZ = ops.spmm(self.H, dP, out=self._operand("Z", N, h))
         ops.gemm(self._in, dZ, transA=True, out=self._grad("W", self.W))
         ops.gemm(self._in, dG, transA=True, out=self._grad("Wg", self.Wg))
         ops.gemm(dZ, self.W, transB=True, beta=1.0, out=dIn)

@@ -102,6 +102,9 @@ def auto_panel_cols(n_cols, F):
 def spmm(A: CSRMatrix, B, out=None, bias=None, act="identity", accumulate=False, gate=None, carry=None,
          conv_out=None, panel_cols=None):
     """out = epilogue(A @ B) -- gcg_spmm_csr_f32 (S.dot, lasagne_layers.py:26,65,67,84)."""
+    if hasattr(A, "dist_spmm"):        # row-partitioned matrix: all-gather of B overlapped with the local block
+        assert not accumulate
+        return A.dist_spmm(B, out=out, bias=bias, act=act, gate=gate, carry=carry, conv_out=conv_out)
     L = _lib.lib()
     bp, ldb = _mat(B, "B")
     n, k = A.shape
@@ -112,6 +115,8 @@ def spmm(A: CSRMatrix, B, out=None, bias=None, act="identity", accumulate=False,
         out = alloc_mat(n, F, B.device)
     if out.shape != (n, F):
         raise ValueError("spmm: out has shape %s, expected %s" % (tuple(out.shape), (n, F)))
+    if n == 0:
+        return out
     cp, ldc = _mat(out, "out")
     gp = hp = vp = None
     ldg = ldh = ldv = 0
@@ -159,6 +164,8 @@ def gemm(A, B, out=None, transA=False, transB=False, beta=0.0, bias=None, act="i
         out = alloc_mat(M, N, A.device)
     if out.shape != (M, N):
         raise ValueError("gemm: out has shape %s, expected %s" % (tuple(out.shape), (M, N)))
+    if M == 0 or N == 0:
+        return out
     cp, ldc = _mat(out, "out")
     mp, ldm = (None, 0) if mask is None else _mat(mask, "mask")
     if mode is None:

@@ -175,7 +175,7 @@ class CSRMatrix:
 
 
 def as_csr(x, device="cuda", long_row_threshold=256) -> CSRMatrix:
-    if isinstance(x, CSRMatrix):
+    if isinstance(x, CSRMatrix) or hasattr(x, "dist_spmm"):      # device CSR or a row-partitioned one
         return x
     return CSRMatrix.from_scipy(x, device=device, long_row_threshold=long_row_threshold)
 
