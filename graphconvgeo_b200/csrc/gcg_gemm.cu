@@ -10,24 +10,11 @@
 #include <algorithm>
 
 #include "gcg_common.cuh"
+#include "gcg_gemm.cuh"
 
 namespace gcg {
 
 constexpr int BM = 128, BN = 128, BK = 16, PAD = 4;
-
-struct GemmArgs {
-  const float* A; int64_t lda;
-  const float* B; int64_t ldb;
-  float* C; int64_t ldc;
-  int64_t M, N, K;
-  float beta;
-  const float* bias; int act;
-  const float* mask; int64_t ld_mask; int mask_act;
-  int n_tiles_n;
-  int split_k; int64_t k_per_split;
-  float* part;  // split-K partials [split][M][N]
-  int vecA, vecB, vecC;
-};
 
 // 4 consecutive elements along the contiguous dimension, zero padded.
 __device__ __forceinline__ float4 load4(const float* __restrict__ base, int64_t outer, int64_t inner,
@@ -41,14 +28,6 @@ __device__ __forceinline__ float4 load4(const float* __restrict__ base, int64_t 
   if (inner + 2 < n_inner) r.z = __ldg(p + 2);
   if (inner + 3 < n_inner) r.w = __ldg(p + 3);
   return r;
-}
-
-__device__ __forceinline__ float gemm_epilogue(const GemmArgs& g, float v, int64_t m, int64_t n) {
-  if (g.beta != 0.f) v += g.beta * g.C[m * g.ldc + n];
-  if (g.bias) v += __ldg(g.bias + n);
-  v = apply_act(v, g.act);
-  if (g.mask) v *= act_grad_from_out(g.mask[m * g.ld_mask + n], g.mask_act);
-  return v;
 }
 
 template <bool TA, bool TB>
@@ -189,17 +168,27 @@ static int auto_split(int64_t M, int64_t N, int64_t K) {
   return (int)std::max<int64_t>(1, std::min<int64_t>(s, 256));
 }
 
+int launch_splitk_reduce(const GemmArgs& g, cudaStream_t st) {
+  const unsigned rg = (unsigned)std::min<int64_t>(ceil_div(g.M * g.N, 256), (int64_t)kNumSMs * 16);
+  gemm_splitk_reduce_kernel<<<rg, 256, 0, st>>>(g);
+  GCG_LAUNCH_CHECK();
+  return GCG_OK;
+}
+
 }  // namespace gcg
 
 using namespace gcg;
 
 extern "C" int64_t gcg_gemm_workspace_bytes(int transA, int transB, int64_t M, int64_t N, int64_t K,
                                             int mode, int32_t split_k) {
-  (void)transA; (void)transB; (void)mode;
   if (M <= 0 || N <= 0 || K <= 0) return 0;
-  if (split_k <= 0) split_k = auto_split(M, N, K);
-  if (split_k <= 1) return 0;
-  return (int64_t)split_k * M * N * (int64_t)sizeof(float);
+  int64_t fma_bytes = 0;
+  {
+    int s = split_k <= 0 ? auto_split(M, N, K) : split_k;
+    if (s > 1) fma_bytes = (int64_t)s * M * N * (int64_t)sizeof(float);
+  }
+  if (mode == GCG_GEMM_FMA) return fma_bytes;
+  return std::max(fma_bytes, gemm_tc_workspace_bytes(transA, transB, M, N, K, mode, split_k));
 }
 
 extern "C" int gcg_gemm_f32(int transA, int transB, int64_t M, int64_t N, int64_t K,
@@ -214,7 +203,8 @@ extern "C" int gcg_gemm_f32(int transA, int transB, int64_t M, int64_t N, int64_
                   (long long)lda, (long long)ldb, (long long)ldc);
   GCG_CHECK_ARG(act >= GCG_ACT_IDENTITY && act <= GCG_ACT_SIGMOID, "gcg_gemm_f32: bad act %d", act);
   GCG_CHECK_ARG(!mask || ld_mask >= N, "gcg_gemm_f32: ld_mask too small");
-  GCG_CHECK_ARG(mode == GCG_GEMM_FMA, "gcg_gemm_f32: mode %d not available in this build", mode);
+  GCG_CHECK_ARG(mode == GCG_GEMM_FMA || mode == GCG_GEMM_TF32X3 || mode == GCG_GEMM_TF32,
+                "gcg_gemm_f32: unknown mode %d", mode);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (M == 0 || N == 0) return GCG_OK;
 
@@ -226,8 +216,19 @@ extern "C" int gcg_gemm_f32(int transA, int transB, int64_t M, int64_t N, int64_
   g.vecA = aligned16(A) && lda % 4 == 0;
   g.vecB = aligned16(B) && ldb % 4 == 0;
   g.vecC = aligned16(C) && ldc % 4 == 0;
+  const int32_t split_req = split_k;
+  if (mode != GCG_GEMM_FMA && K > 0) {
+    g.split_k = split_req > 0 ? split_req : gemm_tc_auto_split(M, N, K);
+    g.k_per_split = 0;
+    g.part = nullptr;
+    const int rc = gemm_tc_launch(g, transA, transB, mode, workspace, workspace_bytes, st);
+    if (rc != GCG_ERR_UNSUPPORTED) return rc;     // ran (or failed hard) on the tensor cores
+  }
   if (split_k <= 0) split_k = auto_split(M, N, K);
   if (K == 0) split_k = 1;
+  if (split_k > 1 && (!workspace || workspace_bytes < (int64_t)split_k * M * N * (int64_t)sizeof(float)) &&
+      mode != GCG_GEMM_FMA)
+    split_k = 1;                                  // FFMA fallback of a tensor-core request: no spare workspace
   g.split_k = split_k;
   g.k_per_split = std::max<int64_t>(BK, ceil_div(ceil_div(std::max<int64_t>(K, 1), split_k), BK) * BK);
   g.split_k = (int)std::max<int64_t>(1, ceil_div(std::max<int64_t>(K, 1), g.k_per_split));

@@ -27,6 +27,14 @@ _GEMM_MODE = os.environ.get("GCG_GEMM_MODE", "auto")     # "fma" | "tf32x3" | "t
 _tc_available = None
 
 
+def set_gemm_mode(mode):
+    """"auto" (tcgen05 3xTF32 for contraction-bound shapes, FFMA otherwise) | "fma" | "tf32x3" | "tf32"."""
+    global _GEMM_MODE
+    if mode != "auto" and mode not in _lib.GEMM_MODE:
+        raise ValueError("unknown gemm mode %r" % (mode,))
+    _GEMM_MODE = mode
+
+
 def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 

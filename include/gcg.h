@@ -134,6 +134,10 @@ int gcg_gemm_f32(int transA, int transB, int64_t M, int64_t N, int64_t K,
                  void* stream);
 int64_t gcg_gemm_workspace_bytes(int transA, int transB, int64_t M, int64_t N,
                                  int64_t K, int mode, int32_t split_k);
+/* 1 when the tcgen05 engines (GCG_GEMM_TF32X3 / GCG_GEMM_TF32) can run: sm_100 device and
+ * a driver that exports cuTensorMapEncodeTiled.  Requests that cannot be described by TMA
+ * tensor maps (unaligned base or leading dimension) fall back to the FFMA tiles. */
+int gcg_gemm_tc_available(void);
 
 /* ------------------------------------------------- epilogues / reductions */
 

@@ -201,3 +201,41 @@ def test_node_reordering_changes_no_result(mode):
     assert_close(m.predict_proba("test"), ref, atol=1e-6)
     emb = m.get_embedding(w.dev_indices[:7])
     assert emb.shape == (7, w.hidden)
+
+
+@pytest.mark.parametrize("n_layers,highway", [(2, False), (3, True)])
+def test_training_step_with_tensor_core_gemms(n_layers, highway):
+    """Same parity check with every dense projection forced onto the tcgen05 3xTF32 engine (the engine
+    the large benchmarks use).  The tensor core's round-toward-zero accumulation costs ~3e-5 of the
+    output magnitude, so the absolute part of the tolerance is 4e-6 here instead of 1e-6."""
+    from graphconvgeo_b200 import _lib, ops
+    if not (_lib.lib().gcg_gemm_tc_available()):
+        pytest.skip("tcgen05 engine unavailable")
+    w = workload("geotext")
+    rng = np.random.RandomState(2)
+    params = go.init_params(rng, w.X.shape[1], w.hidden, w.n_classes, n_layers, highway)
+    net = go.GCNOracle(w.X, w.A_hat, n_layers, highway, (1e-6, 1e-6))
+    y = w.Y[w.train_indices].astype(np.int32)
+    loss, acc, grads, cache = net.loss_and_grads(params, w.train_indices, y)
+    ops.set_gemm_mode("tf32x3")
+    try:
+        m = make_model(w, n_layers, highway, params, w.train_indices, reg=(1e-6, 1e-6))
+        ops.launch_count(reset=True)
+        m.f_train()
+        torch.cuda.synchronize()
+    finally:
+        ops.set_gemm_mode("auto")
+    l_gpu, a_gpu = m.train_results()
+    assert abs(l_gpu - float(loss)) <= 1e-5 * abs(float(loss))
+    for i, ly in enumerate(m.layers[:-1]):
+        assert_close(m.node_rows(ly._out), cache["A"][i], atol=4e-6, what="activation %d" % i)
+    assert_close(m.l_out._out.cpu().numpy(), cache["logits"], atol=4e-6, what="logits")
+    gpu_grads = m.get_grad_values()
+    k = 0
+    for ly in m.layers:
+        for name, t, tags in ly.params:
+            g = gpu_grads[k]
+            if tags.get("regularizable"):
+                g = g + np.float32(0.5e-6) * (np.sign(params[k]) + np.float32(2) * params[k])
+            assert_close(g, grads[k], atol=4e-6, what="grad %d (%s)" % (k, name))
+            k += 1
