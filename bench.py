@@ -235,6 +235,8 @@ def run_gpu(args):
     launches = ops.launch_count(reset=True)
     m._graph = m_graph
 
+    breakdown = op_breakdown(m, dev) if (args.breakdown and world == 1) else None
+
     # ---------------- e2e: host inputs re-uploaded every epoch, loss/acc read back
     e2e = None
     if world == 1:
@@ -274,9 +276,65 @@ def run_gpu(args):
         line["spmm"] = roof["detail"]
     if cpu is not None:
         line["cpu_baseline"] = cpu
+    if breakdown is not None:
+        line["breakdown"] = breakdown
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def op_breakdown(m, dev):
+    """One eager epoch with CUDA events around every libgcg call (warm, in situ): where the epoch goes."""
+    import torch
+    from graphconvgeo_b200 import ops
+    names = ["spmm", "gemm", "colsum", "act_bwd", "highway_bwd", "softmax_ce", "sum_scaled", "scatter_rows"]
+    orig = {n: getattr(ops, n) for n in names}
+    rec = []
+
+    def wrap(n, fn):
+        def inner(*a, **k):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            r = fn(*a, **k)
+            e.record()
+            if n == "spmm":
+                A, B = a[0], a[1]
+                tag = "spmm %dx%d nnz=%d F=%d%s" % (A.shape[0], A.shape[1], getattr(A, "nnz", 0), B.shape[1],
+                                                    " +gate" if k.get("gate") is not None else "")
+            elif n == "gemm":
+                A, B = a[0], a[1]
+                tag = "gemm %s%s A%s B%s" % ("T" if k.get("transA") else "N", "T" if k.get("transB") else "N",
+                                              tuple(A.shape), tuple(B.shape))
+            else:
+                tag = n + " " + "x".join(str(d) for d in a[0].shape)
+            rec.append((tag, s, e))
+            return r
+        return inner
+
+    g, m._graph = m._graph, None
+    try:
+        for n in names:
+            setattr(ops, n, wrap(n, orig[n]))
+        s0, e0 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        m._train_step_enqueue()
+        e0.record()
+        torch.cuda.synchronize(dev)
+    finally:
+        for n in names:
+            setattr(ops, n, orig[n])
+        m._graph = g
+    agg = {}
+    for tag, s, e in rec:
+        a = agg.setdefault(tag, [0, 0.0])
+        a[0] += 1
+        a[1] += s.elapsed_time(e)
+    total = s0.elapsed_time(e0)
+    rows = sorted(agg.items(), key=lambda kv: -kv[1][1])
+    log("---- op breakdown of one eager epoch: %.2f ms total ----" % total)
+    for tag, (c, t) in rows:
+        log("  %-70s x%-2d %8.3f ms  %5.1f%%" % (tag, c, t, 100 * t / total))
+    return {"epoch_ms_eager": total, "ops": [{"op": tag, "calls": c, "ms": t} for tag, (c, t) in rows]}
 
 
 def measure_e2e(m, args, dev, flush):
@@ -360,6 +418,7 @@ def main():
     ap.add_argument("--highway", type=int, default=1)
     ap.add_argument("--random-graph", action="store_true", help="Chung-Lu graph without community structure")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--breakdown", action="store_true", help="per-op CUDA-event breakdown of one eager epoch")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

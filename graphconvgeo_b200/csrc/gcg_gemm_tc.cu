@@ -17,13 +17,16 @@
 //               ring slot / publishes the accumulator
 //   warp 2      TMEM allocator (2 accumulator stages x 128 columns)
 //   warps 4-7   epilogue: tcgen05.ld 32x32b.x32 -> registers -> bias/act/mask -> global,
-//               overlapped with the next tile's main loop through the second TMEM stage
+//               overlapped with the next tile's main loop through the second TMEM stage.
+//               The accumulator holds the TRANSPOSED tile (operands swapped at issue) so that a
+//               warp's lanes are consecutive columns of C: all epilogue traffic is coalesced.
 // Both operand majors are handled by descriptors (K-major and MN-major SWIZZLE_128B canonical
 // layouts), so NN / TN / NT / TT need no transposes.  Split-K (weight gradients: K = #nodes)
 // writes per-slice partials that are reduced in fixed order (deterministic).
 #include <cuda.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "gcg_gemm.cuh"
 
@@ -33,7 +36,7 @@ constexpr int TM = 128, TN = 128, TK = 32;       // CTA tile; TK*4 B = the 128 B
 constexpr int UK = 8;                            // K of one tcgen05.mma.kind::tf32
 constexpr int TILE_BYTES = TM * TK * 4;          // 16 KB per operand tile
 constexpr int ACC_STAGES = 2;
-constexpr int TMEM_COLS = ACC_STAGES * TN;       // 256 (power of two)
+constexpr int TMEM_COLS = ACC_STAGES * TM;       // 256 (power of two): D^T tile = TN lanes x TM columns
 constexpr int TC_THREADS = 256;
 
 int launch_splitk_reduce(const GemmArgs& g, cudaStream_t st);   // gcg_gemm.cu
@@ -103,6 +106,16 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
   d |= (uint64_t)1 << 46;                                       // descriptor version (Blackwell)
   d |= (uint64_t)(MN ? 1 : 2) << 61;                            // SWIZZLE_128B_BASE32B : SWIZZLE_128B
   return d;
+}
+
+// compact (non-inlined) activation for the general epilogue path: keeps the unrolled body small
+__device__ __noinline__ float epi_act(float x, int act) {
+  switch (act) {
+    case GCG_ACT_RELU: return fmaxf(x, 0.f);
+    case GCG_ACT_TANH: return tanhf(x);
+    case GCG_ACT_SIGMOID: return 1.f / (1.f + expf(-x));
+    default: return x;
+  }
 }
 
 struct TcArgs {
@@ -197,8 +210,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
     // ======================================================================= MMA issuer
     if (lane == 0) {
       // instruction descriptor: D=F32 (c_format 1), A/B = TF32 (2), majors, N>>3, M>>4
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) |
-                             ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+      // Operands are SWAPPED: the UMMA "A" (M side, TMEM lanes) is our B tile (n), the UMMA "B" (N side,
+      // TMEM columns) is our A tile (m), i.e. the accumulator holds C^T -- see the epilogue.
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((B_MN ? 1u : 0u) << 15) |
+                             ((A_MN ? 1u : 0u) << 16) | ((uint32_t)(TM >> 3) << 17) | ((uint32_t)(TN >> 4) << 24);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -206,7 +221,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
         const int kb0 = z * a.kb_per_split, kb1 = min(a.num_kb_total, kb0 + a.kb_per_split);
         mbar_wait(acc_empty + acc, acc_phase ^ 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t d_tmem = tmem_base + acc * TN;
+        const uint32_t d_tmem = tmem_base + acc * TM;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(full + stage, phase);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -223,11 +238,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
             if (a.x3) {
               const uint64_t al = make_desc<A_MN>(sA + TILE_BYTES + aoff);
               const uint64_t bl = make_desc<B_MN>(sB + TILE_BYTES + boff);
-              umma_tf32(d_tmem, al, bh, idesc, first);   // small terms first
-              umma_tf32(d_tmem, ah, bl, idesc, 1u);
-              umma_tf32(d_tmem, ah, bh, idesc, 1u);
+              umma_tf32(d_tmem, bh, al, idesc, first);   // small terms first
+              umma_tf32(d_tmem, bl, ah, idesc, 1u);
+              umma_tf32(d_tmem, bh, ah, idesc, 1u);
             } else {
-              umma_tf32(d_tmem, ah, bh, idesc, first);
+              umma_tf32(d_tmem, bh, ah, idesc, first);
             }
           }
           umma_commit(empty + stage);                    // frees the ring slot when the MMAs retire
@@ -239,44 +254,114 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
     }
   } else if (warp >= 4) {
     // ========================================================================= epilogue
+    // The MMA computes the TRANSPOSED tile D[n][m] (operands swapped, see the issuer), so a TMEM
+    // lane -- hence a thread -- is a column n of C and its registers run along m: for a fixed m
+    // the 32 lanes of a warp touch 32 consecutive floats of one row of C -> every global access
+    // of the epilogue (C, beta*C, bias, mask, split-K partials) is a single 128 B wavefront.
     const GemmArgs& g = a.g;
     const int ew = warp & 3;                             // TMEM lane quarter owned by this warp
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int nt = t % a.n_tiles, mt = (t / a.n_tiles) % a.m_tiles, z = t / (a.n_tiles * a.m_tiles);
-      const int64_t m = (int64_t)mt * TM + ew * 32 + lane;
-      const int64_t n0 = (int64_t)nt * TN;
+      const int64_t n = (int64_t)nt * TN + ew * 32 + lane;
+      const int64_t m0 = (int64_t)mt * TM;
+      const bool n_ok = n < g.N;
+      const float bias_n = (g.bias && n_ok && a.splits == 1) ? __ldg(g.bias + n) : 0.f;
+      const bool relu = g.act == GCG_ACT_RELU;
+      const bool simple = g.beta == 0.f && g.mask == nullptr && (g.act == GCG_ACT_IDENTITY || relu);
+      const bool gate_like = g.beta == 0.f && g.mask == nullptr && g.act == GCG_ACT_SIGMOID;
+      const bool accum_like = g.act == GCG_ACT_IDENTITY && g.bias == nullptr &&
+                              (g.mask == nullptr || g.mask_act == GCG_ACT_RELU || g.mask_act == GCG_ACT_TANH);
       mbar_wait(acc_full + acc, acc_phase);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
-      for (int c = 0; c < TN; c += 32) {
+      for (int c = 0; c < TM; c += 32) {
         uint32_t v[32];
-        tmem_ld32(tmem_base + acc * TN + c + ((uint32_t)(ew * 32) << 16), v);
+        tmem_ld32(tmem_base + acc * TM + c + ((uint32_t)(ew * 32) << 16), v);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (m < g.M) {
-          const int64_t nb = n0 + c;
-          if (a.splits > 1) {
-            float* dst = g.part + ((int64_t)z * g.M + m) * g.N + nb;
+        // The bodies below are kept tiny on purpose: the 32-way unroll is needed to keep v[] in
+        // registers, and a fat per-element body (bounds + beta + act switch + mask) made the kernel
+        // 85 KB of SASS whose instruction-cache misses cost 27 us per tile (ncu: no_instruction stalls).
+        const int64_t mrow = m0 + c;
+        const int rows = (int)min((int64_t)32, g.M - mrow);
+        if (!n_ok || rows <= 0) continue;
+        if (a.splits > 1) {
+          float* dst = g.part + ((int64_t)z * g.M + mrow) * g.N + n;
+          if (rows == 32) {
 #pragma unroll
-            for (int e = 0; e < 32; ++e)
-              if (nb + e < g.N) dst[e] = __uint_as_float(v[e]);
+            for (int e = 0; e < 32; ++e) { *dst = __uint_as_float(v[e]); dst += g.N; }
           } else {
-            float* dst = g.C + m * g.ldc + nb;
 #pragma unroll
-            for (int e4 = 0; e4 < 32; e4 += 4) {
-              float o[4];
+            for (int e = 0; e < 32; ++e) { if (e < rows) *dst = __uint_as_float(v[e]); dst += g.N; }
+          }
+        } else if (simple) {
+          float* dst = g.C + mrow * g.ldc + n;
+          if (rows == 32) {
 #pragma unroll
-              for (int e = 0; e < 4; ++e)
-                o[e] = (nb + e4 + e < g.N) ? gemm_epilogue(g, __uint_as_float(v[e4 + e]), m, nb + e4 + e) : 0.f;
-              if (g.vecC && nb + e4 + 3 < g.N) {
-                *reinterpret_cast<float4*>(dst + e4) = make_float4(o[0], o[1], o[2], o[3]);
-              } else {
-#pragma unroll
-                for (int e = 0; e < 4; ++e)
-                  if (nb + e4 + e < g.N) dst[e4 + e] = o[e];
-              }
+            for (int e = 0; e < 32; ++e) {
+              const float o = __uint_as_float(v[e]) + bias_n;
+              *dst = relu ? fmaxf(o, 0.f) : o;
+              dst += g.ldc;
             }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+              const float o = __uint_as_float(v[e]) + bias_n;
+              if (e < rows) *dst = relu ? fmaxf(o, 0.f) : o;
+              dst += g.ldc;
+            }
+          }
+        } else if (gate_like) {
+          // act(x + bias) with act = sigmoid (the highway gate), beta = 0, no mask
+          float* dst = g.C + mrow * g.ldc + n;
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            const float o = __fdividef(1.f, 1.f + __expf(-(__uint_as_float(v[e]) + bias_n)));
+            if (e < rows) *dst = o;
+            dst += g.ldc;
+          }
+        } else if (accum_like) {
+          // (x + beta*C) [* act'(mask)], identity activation: the backward dH products
+          float* dst = g.C + mrow * g.ldc + n;
+          const float* msk = g.mask ? g.mask + mrow * g.ld_mask + n : dst;
+          const int64_t mstep = g.mask ? g.ld_mask : g.ldc;
+          const bool has_mask = g.mask != nullptr, mrelu = g.mask_act == GCG_ACT_RELU;
+          const bool has_beta = g.beta != 0.f;
+          // two phases per half chunk: all loads first (16 independent 128 B wavefronts in flight),
+          // then the math and the stores -- a load/store-interleaved loop serialises on possible aliasing
+#pragma unroll
+          for (int h = 0; h < 32; h += 16) {
+            float cv[16], mk[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              const bool ok = (h + e) < rows;
+              cv[e] = (has_beta && ok) ? __ldcg(dst + (int64_t)e * g.ldc) : 0.f;
+              mk[e] = (has_mask && ok) ? __ldcg(msk + (int64_t)e * mstep) : 1.f;
+            }
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              float o = fmaf(g.beta, cv[e], __uint_as_float(v[h + e]));
+              if (has_mask) o *= mrelu ? (mk[e] > 0.f ? 1.f : 0.f) : (1.f - mk[e] * mk[e]);
+              if ((h + e) < rows) dst[(int64_t)e * g.ldc] = o;
+            }
+            dst += 16 * g.ldc;
+            msk += 16 * mstep;
+          }
+        } else {
+          float* dst = g.C + mrow * g.ldc + n;
+          const float* msk = g.mask ? g.mask + mrow * g.ld_mask + n : nullptr;
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            if (e < rows) {
+              float o = __uint_as_float(v[e]);
+              if (g.beta != 0.f) o = fmaf(g.beta, *dst, o);
+              o = epi_act(o + bias_n, g.act);
+              if (msk) o *= act_grad_from_out(*msk, g.mask_act);
+              *dst = o;
+            }
+            dst += g.ldc;
+            if (msk) msk += g.ld_mask;
           }
         }
       }
