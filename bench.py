@@ -165,6 +165,11 @@ def run_gpu(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly one JSON line: libraries (NCCL prints its version banner there) are
+    # redirected to stderr for the duration of the run
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if world != args.gpus:
         if world == 1 and args.gpus > 1:
             raise SystemExit("launch with torchrun --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus))
@@ -182,7 +187,7 @@ def run_gpu(args):
                         n_layers=args.layers, highway=bool(args.highway), seed=1, device=dev, cuda_graph=True)
     if world > 1:
         from graphconvgeo_b200.dist import DistMLPCONV
-        m = DistMLPCONV(**model_kwargs)
+        m = DistMLPCONV(partition=args.partition, **model_kwargs)
     else:
         m = MLPCONV(**model_kwargs)
     t0 = time.time()
@@ -264,7 +269,8 @@ def run_gpu(args):
         "config": dict(bench_config(args), nodes=wl.meta["n"], vocab=wl.meta["vocab"], hidden=wl.hidden,
                        regions=wl.n_classes, nnz_A=wl.meta["nnz_A"], nnz_X=wl.meta["nnz_X"],
                        max_degree=wl.meta["max_degree"], graph="community" if wl.meta["community"] else "chung-lu",
-                       parallelism="row-partition x%d" % world if world > 1 else "single GPU",
+                       parallelism=("rows x%d, A_hat.Z %s" % (world, "feature-sliced + all-to-all" if args.partition == "feature"
+                                                              else "row blocks + all-gather")) if world > 1 else "single GPU",
                        gemm_mode=os.environ.get("GCG_GEMM_MODE", "auto")),
         "clocks": sampler.summary(), "gpu_launches": launches * args.steps,
         "launches_per_epoch": launches, "loss": loss, "acc": acc,
@@ -278,7 +284,8 @@ def run_gpu(args):
         line["cpu_baseline"] = cpu
     if breakdown is not None:
         line["breakdown"] = breakdown
-    print(json.dumps(line), flush=True)
+    sys.stdout.flush()
+    os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
@@ -380,6 +387,9 @@ def spmm_roofline(m, wl, dev, reps=10):
     n_in = A.shape[1]
     # compulsory traffic of this rank's launch(es): CSR once, the gathered operand once, the output once
     alg_bytes = 8 * nnz + 4 * (N + 1) + 4 * n_in * F + 4 * N * F
+    if hasattr(A, "full"):      # feature-sliced: all rows, F/P columns on this rank (+ the two all-to-alls, timed too)
+        fp = (-(-F // A.part.world) + 3) // 4 * 4
+        alg_bytes = 8 * nnz + 4 * (n_in + 1) + 8 * n_in * fp
     results = {}
     dist_mode = hasattr(A, "dist_spmm")
     for label, panel in ((("auto", None),) if dist_mode else (("auto", None), ("rows", 0))):
@@ -419,6 +429,8 @@ def main():
     ap.add_argument("--random-graph", action="store_true", help="Chung-Lu graph without community structure")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--breakdown", action="store_true", help="per-op CUDA-event breakdown of one eager epoch")
+    ap.add_argument("--partition", default="feature", choices=["feature", "row"],
+                    help="multi-GPU scheme for A_hat.Z: feature slices + all-to-all, or row blocks + all-gather")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -45,6 +45,7 @@ PROTOTYPES = {
     "gcg_colsum_f32": (c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_i64, c_vp]),
     "gcg_colsum_workspace_bytes": (c_i64, [c_i64, c_i64]),
     "gcg_act_bwd_f32": (c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_int, c_vp]),
+    "gcg_highway_fwd_f32": (c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_vp]),
     "gcg_highway_bwd_f32": (c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp,
                                     c_i64, c_vp, c_i64, c_i64, c_i64, c_int, c_vp]),
     "gcg_softmax_ce_f32": (c_int, [c_vp, c_i64, c_vp, c_i64, c_i64, c_f32, c_vp, c_i64, c_vp, c_i64, c_vp,

@@ -143,6 +143,25 @@ __global__ void __launch_bounds__(256) highway_bwd_kernel(
   }
 }
 
+// --------------------------------------------------------------- highway_fwd
+// O = g*Hc + (1-g)*Hin with separately rounded operations (same arithmetic as the fused SpMM epilogue)
+template <int VEC>
+__global__ void __launch_bounds__(256) highway_fwd_kernel(const float* __restrict__ Hc, int64_t ld_hc,
+                                                          const float* __restrict__ g, int64_t ld_g,
+                                                          const float* __restrict__ Hin, int64_t ld_hin,
+                                                          float* O, int64_t ld_o, int64_t n_rows, int64_t W) {
+  const int64_t total = n_rows * W;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / W, c = (i - r * W) * VEC;
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+      const float gg = g[r * ld_g + c + e], hc = Hc[r * ld_hc + c + e], hi = Hin[r * ld_hin + c + e];
+      O[r * ld_o + c + e] = __fadd_rn(__fmul_rn(gg, hc), __fmul_rn(__fsub_rn(1.f, gg), hi));
+    }
+  }
+}
+
 // ------------------------------------------------------------- softmax + CE
 // one warp per target row; the row (<= a few KB) is re-read from L1.
 __global__ void __launch_bounds__(256) softmax_ce_kernel(
@@ -536,6 +555,21 @@ extern "C" int gcg_elastic_net_f32(int32_t n_tensors, const float* const* h_para
     GCG_LAUNCH_CHECK();
   }
   sum_kernel<<<1, 1024, 0, st>>>(part, blocks, 1.f, out);
+  GCG_LAUNCH_CHECK();
+  return GCG_OK;
+}
+
+extern "C" int gcg_highway_fwd_f32(const float* Hc, int64_t ld_hc, const float* g, int64_t ld_g,
+                                   const float* Hin, int64_t ld_hin, float* O, int64_t ld_o,
+                                   int64_t n_rows, int64_t F, void* stream) {
+  GCG_CHECK_ARG(Hc && g && Hin && O, "gcg_highway_fwd_f32: NULL argument");
+  GCG_CHECK_SHAPE(F > 0 && ld_hc >= F && ld_g >= F && ld_hin >= F && ld_o >= F, "gcg_highway_fwd_f32: bad leading dimension");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (n_rows == 0) return GCG_OK;
+  if (vec_ok(F, {{Hc, ld_hc}, {g, ld_g}, {Hin, ld_hin}, {O, ld_o}}))
+    highway_fwd_kernel<4><<<grid_for(n_rows * ((F + 3) / 4), 256), 256, 0, st>>>(Hc, ld_hc, g, ld_g, Hin, ld_hin, O, ld_o, n_rows, (F + 3) / 4);
+  else
+    highway_fwd_kernel<1><<<grid_for(n_rows * F, 256), 256, 0, st>>>(Hc, ld_hc, g, ld_g, Hin, ld_hin, O, ld_o, n_rows, F);
   GCG_LAUNCH_CHECK();
   return GCG_OK;
 }

@@ -73,6 +73,8 @@ struct SpmmArgs {
   int n_panels;
   int seg_blocks;
   int row_blocks;
+  int nnz_total;
+  int only_segments;   // vec kernel launched for the long-row segments only (rows go to the bulk-copy kernel)
 };
 
 __device__ __forceinline__ float4 f4_axpy_exact(float4 acc, float v, float4 x) {
@@ -149,7 +151,7 @@ __global__ void __launch_bounds__(256) spmm_vec_kernel(const SpmmArgs a) {
     if (r >= a.n_rows) return;
     beg = __ldg(a.indptr + r);
     end = __ldg(a.indptr + r + 1);
-    if (end - beg > a.long_thresh) return;  // segment blocks + finalize own this row
+    if (a.only_segments || end - beg > a.long_thresh) return;  // segment blocks + finalize own this row
     row = r;
     is_seg = false;
   }
@@ -279,6 +281,135 @@ __global__ void __launch_bounds__(256) spmm_scalar_kernel(const SpmmArgs a) {
       *cp = v;
     }
   }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Bulk-copy (TMA) staged variant: whole rows per warp, gathered rows land in shared memory.
+//
+// The register-gather kernel above can only keep U*VPL 16-byte loads per lane in flight (126
+// registers -> 16 warps/SM -> ~50 KB in flight per SM, ncu: 16 % warps active, DRAM 43 % busy).
+// Here every gathered dense row (F*4 contiguous bytes) is fetched by ONE cp.async.bulk
+// (global -> shared, mbarrier complete_tx) issued by lane 0, into a per-warp ring of RING slots:
+// 8 warps x 8 slots x 2400 B = 154 KB of gathers in flight per SM with no register cost.  A warp
+// owns `rows_per_warp` CONSECUTIVE rows, so its non-zeros are one contiguous CSR slice that is
+// streamed without draining the ring at row boundaries; column indices / values are fetched 32 at
+// a time (plus a prefetched next chunk) and broadcast by shuffle.  Accumulation order and rounding
+// are identical to the register kernel (CSR order, __fmul_rn/__fadd_rn) -> bit-identical results.
+// Long rows are skipped here; their segments run in spmm_vec_kernel (only_segments) + finalize.
+__device__ __forceinline__ uint32_t sm_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sm_u32(bar)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(sm_u32(dst)), "l"(src), "r"(bytes), "r"(sm_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "W_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra D_%=;\n\t"
+      "bra W_%=;\n\t"
+      "D_%=:\n\t"
+      "}" ::"r"(sm_u32(bar)), "r"(parity) : "memory");
+}
+
+// first non-empty, non-long row at or after r (warp-uniform)
+__device__ __forceinline__ bool seek_row(const SpmmArgs& a, int& r, int& k, int& kend, int r1) {
+  while (r < r1) {
+    const int b = __ldg(a.indptr + r), e = __ldg(a.indptr + r + 1);
+    if (e > b && (e - b) <= a.long_thresh) { k = b; kend = e; return true; }
+    ++r;
+  }
+  return false;
+}
+
+template <int VPL>
+__global__ void __launch_bounds__(256, 1)
+spmm_tma_kernel(const SpmmArgs a, const int rows_per_warp, const int ring, const int slot_bytes) {
+  extern __shared__ __align__(128) uint8_t smem_dyn[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint8_t* slots = smem_dyn + (size_t)warp * ring * slot_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_dyn + (size_t)8 * ring * slot_bytes) + warp * ring;
+  if (lane == 0) {
+    for (int s = 0; s < ring; ++s)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(sm_u32(bars + s)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  const int r0 = (blockIdx.x * 8 + warp) * rows_per_warp;
+  const int r1 = min(a.n_rows, r0 + rows_per_warp);
+  if (r0 >= a.n_rows) return;
+  const uint64_t strm = policy_evict_first();
+  const uint32_t row_bytes = (uint32_t)a.f4_total * 16u;
+  bool cv[VPL];
+#pragma unroll
+  for (int j = 0; j < VPL; ++j) cv[j] = (lane + 32 * j) < a.f4_total;
+
+  // ---- producer cursor (column indices) with a prefetched next chunk
+  int pr = r0, pk = 0, pend = 0;
+  bool pvalid = seek_row(a, pr, pk, pend, r1);
+  int pbase = pvalid ? pk : 0;
+  auto ld_idx = [&](int base) { const int q = base + lane; return q < a.nnz_total ? ldg_i32_stream(a.indices + q, strm) : 0; };
+  auto ld_val = [&](int base) { const int q = base + lane; return q < a.nnz_total ? ldg_f32_stream(a.vals + q, strm) : 0.f; };
+  int pidx = ld_idx(pbase), pidx_nx = ld_idx(pbase + 32);
+  int issued = 0, consumed = 0;
+  auto issue_one = [&]() {
+    if (pk >= pbase + 32 || pk < pbase) {
+      if (pk >= pbase + 32 && pk < pbase + 64) { pbase += 32; pidx = pidx_nx; }
+      else { pbase = pk; pidx = ld_idx(pbase); }
+      pidx_nx = ld_idx(pbase + 32);
+    }
+    const int col = __shfl_sync(0xffffffffu, pidx, pk - pbase);
+    const int slot = issued % ring;
+    if (lane == 0) bulk_g2s(slots + (size_t)slot * slot_bytes, a.B + (int64_t)col * a.ldb, row_bytes, bars + slot);
+    ++issued;
+    if (++pk == pend) { ++pr; pvalid = seek_row(a, pr, pk, pend, r1); }
+  };
+  while (pvalid && issued < ring) issue_one();
+
+  // ---- consumer
+  int cbase = -64;
+  float cval = 0.f, cval_nx = 0.f;
+  for (int r = r0; r < r1; ++r) {
+    const int b = __ldg(a.indptr + r), e = __ldg(a.indptr + r + 1);
+    if (e - b > a.long_thresh) continue;                 // segments + finalize own this row
+    float4 acc[VPL];
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k = b; k < e; ++k) {
+      if (k >= cbase + 32 || k < cbase) {
+        if (k >= cbase + 32 && k < cbase + 64) { cbase += 32; cval = cval_nx; }
+        else { cbase = k; cval = ld_val(cbase); }
+        cval_nx = ld_val(cbase + 32);
+      }
+      const float v = __shfl_sync(0xffffffffu, cval, k - cbase);
+      const int slot = consumed % ring;
+      bar_wait(bars + slot, (uint32_t)((consumed / ring) & 1));
+      const float4* src = reinterpret_cast<const float4*>(slots + (size_t)slot * slot_bytes) + lane;
+#pragma unroll
+      for (int j = 0; j < VPL; ++j)
+        if (cv[j]) acc[j] = f4_axpy_exact(acc[j], v, src[32 * j]);
+      ++consumed;
+      __syncwarp();                                      // every lane is done with the slot
+      if (pvalid) issue_one();                           // refill it (issued % ring == this slot)
+    }
+#pragma unroll
+    for (int j = 0; j < VPL; ++j)
+      if (cv[j]) epilogue_store(a, r, lane + 32 * j, acc[j], strm);
+  }
+}
+
+template <int VPL>
+static cudaError_t launch_tma(const SpmmArgs& a, int rows_per_warp, int ring, int slot_bytes, cudaStream_t st) {
+  const int smem_bytes = 8 * ring * slot_bytes + 8 * ring * 8;
+  cudaError_t e = cudaFuncSetAttribute(spmm_tma_kernel<VPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+  if (e != cudaSuccess) return e;
+  const unsigned grid = (unsigned)ceil_div(a.n_rows, 8 * rows_per_warp);
+  spmm_tma_kernel<VPL><<<grid, 256, smem_bytes, st>>>(a, rows_per_warp, ring, slot_bytes);
+  return cudaGetLastError();
 }
 
 template <int G, int VPL>
@@ -432,6 +563,53 @@ extern "C" int gcg_spmm_csr_f32(const gcg_plan* p, const float* B, int64_t ldb, 
     GCG_CHECK_ARG(aligned16(workspace), "gcg_spmm_csr_f32: workspace must be 16-byte aligned");
   }
 
+  a.nnz_total = (int)p->nnz;
+  a.only_segments = 0;
+  if (panel_cols < 0 && a.f4_total <= 256) {
+    // bulk-copy staged variant: rows here, long-row segments in the register kernel
+    const int slot_bytes = a.f4_total * 16;
+    int ring = std::min(8, (200 * 1024 / 8) / slot_bytes);
+    if (ring >= 2) {
+      const int vpl = (int)ceil_div(a.f4_total, 32);
+      const int rows_per_warp = 16;
+      cudaError_t e2;
+      if (p->n_seg > 0) {
+        SpmmArgs sa = a;
+        sa.only_segments = 1;
+        sa.panel_f4 = 32 * std::min(5, vpl);
+        sa.n_panels = (int)ceil_div(a.f4_total, sa.panel_f4);
+        sa.seg_blocks = (int)ceil_div(p->n_seg, 8);
+        sa.row_blocks = 0;
+        switch (std::min(5, vpl)) {
+          case 1: e2 = launch_vec<32, 1>(sa, st); break;
+          case 2: e2 = launch_vec<32, 2>(sa, st); break;
+          case 3: e2 = launch_vec<32, 3>(sa, st); break;
+          case 4: e2 = launch_vec<32, 4>(sa, st); break;
+          default: e2 = launch_vec<32, 5>(sa, st); break;
+        }
+        if (e2 != cudaSuccess) { set_error("gcg_spmm_csr_f32: segment launch failed: %s", cudaGetErrorString(e2)); return GCG_ERR_CUDA; }
+        count_launch();
+      }
+      switch (vpl) {
+        case 1: e2 = launch_tma<1>(a, rows_per_warp, ring, slot_bytes, st); break;
+        case 2: e2 = launch_tma<2>(a, rows_per_warp, ring, slot_bytes, st); break;
+        case 3: e2 = launch_tma<3>(a, rows_per_warp, ring, slot_bytes, st); break;
+        case 4: e2 = launch_tma<4>(a, rows_per_warp, ring, slot_bytes, st); break;
+        case 5: e2 = launch_tma<5>(a, rows_per_warp, ring, slot_bytes, st); break;
+        case 6: e2 = launch_tma<6>(a, rows_per_warp, ring, slot_bytes, st); break;
+        case 7: e2 = launch_tma<7>(a, rows_per_warp, ring, slot_bytes, st); break;
+        default: e2 = launch_tma<8>(a, rows_per_warp, ring, slot_bytes, st); break;
+      }
+      if (e2 != cudaSuccess) { set_error("gcg_spmm_csr_f32: bulk-copy launch failed: %s", cudaGetErrorString(e2)); return GCG_ERR_CUDA; }
+      count_launch();
+      if (p->n_long > 0) {
+        spmm_finalize_kernel<<<(unsigned)ceil_div(p->n_long, 8), 256, 0, st>>>(a);
+        GCG_LAUNCH_CHECK();
+      }
+      return GCG_OK;
+    }
+  }
+  if (panel_cols < 0) panel_cols = 0;
   // choose (G, VPL): panel width in float4 = G*VPL
   int want_f4 = a.f4_total;
   if (panel_cols > 0) want_f4 = (int)std::min<int64_t>(a.f4_total, std::max<int64_t>(1, (panel_cols + 3) / 4));

@@ -155,12 +155,111 @@ class DistCSRMatrix:
         return ops.spmm(self.off, full, out=out, accumulate=True, **epi)
 
 
+class FeatureSplitCSRMatrix:
+    """Alternative multi-GPU scheme for A_hat.Z (SURVEY 7.2 "feature-partitioned SpMM"): every rank keeps
+    the WHOLE sparse matrix (A_hat is only 8*nnz bytes) and propagates a COLUMN slice Z[:, cols_p] of the
+    dense operand for all nodes, so the SpMM itself needs no communication.  The operand arrives row-
+    partitioned from the local GEMM, so it is transposed with one all-to-all before ([n_loc, F] ->
+    [N, F/P]) and one after the SpMM: each rank sends n_loc*F*(P-1)/P floats per direction -- 8x less than
+    the all-gather of the row-partitioned scheme at P = 8 (measured: DESIGN.md section 5).
+    Output rows are grouped by owner rank (``row_counts``); bias + activation stay fused in the SpMM
+    (they are column-wise), the highway mix runs after the transpose back."""
+
+    def __init__(self, part: RowPartition, full: CSRMatrix, row_counts):
+        self.part = part
+        self.full = full
+        self.row_counts = [int(c) for c in row_counts]
+        self.shape = (self.row_counts[part.rank], part.n_pad)
+        self.long_row_threshold = full.long_row_threshold
+        self.nnz = full.nnz
+        self.diag_fraction = None
+        self.host = full.host
+
+    @property
+    def device(self):
+        return self.part.device
+
+    @classmethod
+    def from_global(cls, A: CSRMatrix, part: RowPartition):
+        ip, ix, d = A._host_arrays()
+        p = np.empty(part.n_pad + 1, np.int32)
+        p[:len(ip)] = ip
+        p[len(ip):] = ip[-1]
+        full = CSRMatrix.from_host((p, ix, d), (part.n_pad, part.n_pad), part.device, A.long_row_threshold)
+        return cls(part, full, [part.n_loc] * part.world)
+
+    def gather_rows_grouped(self, idx_global):
+        """A[idx,:] for ALL target nodes, rows grouped by owner rank (ascending position inside a group)."""
+        idx_global = np.asarray(idx_global, dtype=np.int64)
+        owners = self.part.owner(idx_global)
+        order = np.argsort(owners, kind="stable")
+        counts = np.bincount(owners, minlength=self.part.world)
+        sub = self.full.gather_rows(idx_global[order].astype(np.int32))
+        sub.shape = (sub.shape[0], self.part.n_pad)
+        return FeatureSplitCSRMatrix(self.part, sub, counts)
+
+    def _buf(self, key, shape):
+        k = ("fs", key, tuple(shape))
+        b = self.part._full.get(k)
+        if b is None:
+            b = torch.zeros(shape, dtype=torch.float32, device=self.part.device)
+            self.part._full[k] = b
+        return b
+
+    def dist_spmm(self, B, out=None, bias=None, act="identity", gate=None, carry=None, conv_out=None):
+        part = self.part
+        P, r, n_loc = part.world, part.rank, part.n_loc
+        F = B.shape[1]
+        assert B.shape[0] == n_loc
+        Fp = (-(-F // P) + 3) // 4 * 4
+        my_rows = self.row_counts[r]
+        if out is None:
+            out = ops.alloc_mat(my_rows, F, B.device)
+        # 1. row layout -> column slices (zero padded), one all-to-all
+        send = self._buf("send", (P, n_loc, Fp))
+        for q in range(P):
+            c0 = q * Fp
+            w = max(0, min(Fp, F - c0))
+            if w > 0:
+                send[q, :, :w].copy_(B[:, c0:c0 + w])
+        recv = self._buf("recv", (P * n_loc, Fp))
+        dist.all_to_all_single(recv.view(-1), send.view(-1), group=part.group)
+        part.bytes_gathered += (P - 1) * n_loc * Fp * 4
+        # 2. local SpMM over ALL rows for this rank's columns; bias/act are column-wise -> fused
+        bs = None
+        if bias is not None:
+            bpad = self._buf("bias", (P * Fp,))
+            bpad[:F].copy_(bias)
+            bs = bpad[r * Fp:(r + 1) * Fp]
+        rows_total = int(sum(self.row_counts))
+        outslice = self._buf("outslice", (max(rows_total, 1), Fp))
+        if rows_total > 0:
+            ops.spmm(self.full, recv, out=outslice[:rows_total], bias=bs, act=act)
+        # 3. column slices -> row layout (rows grouped by owner), second all-to-all
+        back = self._buf("back", (P * max(my_rows, 1), Fp))
+        dist.all_to_all_single(back[:P * my_rows], outslice[:rows_total], output_split_sizes=[my_rows] * P,
+                               input_split_sizes=self.row_counts, group=part.group)
+        if my_rows == 0:
+            return out
+        back3 = back[:P * my_rows].view(P, my_rows, Fp)
+        dst = out if gate is None or conv_out is None else conv_out
+        for q in range(P):
+            c0 = q * Fp
+            w = max(0, min(Fp, F - c0))
+            if w > 0:
+                dst[:, c0:c0 + w].copy_(back3[q, :, :w])
+        if gate is not None:
+            ops.highway_mix(dst, gate, carry, out=out)       # out = g*Hc + (1-g)*H ; Hc kept in conv_out
+        return out
+
+
 class DistTargetIndices(L.TargetIndices):
     """The part of a target_indices vector whose nodes this rank owns."""
 
     def __init__(self, idx_global_perm, H: DistCSRMatrix, n_global):   # noqa: super().__init__ not wanted
         part = H.part
         self.sel, self.local = part.local_rows(idx_global_perm)
+        self.idx_global = np.asarray(idx_global_perm)
         self.n = len(self.local)
         self.n_global = int(n_global)
         self.device = part.device
@@ -172,7 +271,10 @@ class DistTargetIndices(L.TargetIndices):
     @property
     def Hsub(self):
         if self._Hsub is None:
-            self._Hsub = self.H.gather_rows(self.local)
+            if hasattr(self.H, "gather_rows_grouped"):
+                self._Hsub = self.H.gather_rows_grouped(self.idx_global)
+            else:
+                self._Hsub = self.H.gather_rows(self.local)
         return self._Hsub
 
     @property
@@ -187,9 +289,11 @@ class DistMLPCONV(MLPCONV):
     single-process fit() is); each keeps its row block.  Results (loss, acc, predictions gathered
     over ranks, parameters) equal the single-GPU ones up to summation order of the all-reduces."""
 
-    def __init__(self, *args, group=None, **kwargs):
+    def __init__(self, *args, group=None, partition="feature", **kwargs):
         kwargs["cuda_graph"] = False          # NCCL work is enqueued eagerly
         super().__init__(*args, **kwargs)
+        assert partition in ("row", "feature")
+        self.partition = partition            # how A_hat.Z is distributed (see the two matrix classes)
         self.group = group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
@@ -224,7 +328,7 @@ class DistMLPCONV(MLPCONV):
         self._node_map = node_map
         part = RowPartition(n, self.world, self.rank, self.device, self.group)
         self.part = part
-        Hd = DistCSRMatrix.from_global(Hg, part)
+        Hd = (FeatureSplitCSRMatrix if self.partition == "feature" else DistCSRMatrix).from_global(Hg, part)
         # local rows of X (padded with empty rows)
         ip, ix, d = Xg._host_arrays()
         p = np.zeros(part.n_loc + 1, np.int32)

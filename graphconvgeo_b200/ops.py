@@ -212,6 +212,16 @@ def act_bwd(dA, A, act, out=None):
     return out
 
 
+def highway_mix(Hc, g, Hin, out=None):
+    """out = g*Hc + (1-g)*Hin -- gcg_highway_fwd_f32 (normally fused into the SpMM epilogue)."""
+    if out is None:
+        out = alloc_mat(Hc.shape[0], Hc.shape[1], Hc.device)
+    a = [_mat(t, nm) for t, nm in ((Hc, "Hc"), (g, "g"), (Hin, "Hin"), (out, "out"))]
+    flat = [x for pair in a for x in pair]
+    _lib.check(_lib.lib().gcg_highway_fwd_f32(*flat, Hc.shape[0], Hc.shape[1], _stream()), "gcg_highway_fwd_f32")
+    return out
+
+
 def highway_bwd(dO, g, Hc, Hin, act, dP=None, dGpre=None, dHin=None):
     L = _lib.lib()
     n, F = dO.shape

@@ -103,7 +103,9 @@ int gcg_plan_info(const gcg_plan* plan, int64_t* info);
  * 16-byte aligned B/C and ldb, ldc multiples of 4 with ld >= round_up(F, 4)
  * (pad columns of C are then overwritten with unspecified values); anything
  * else takes the scalar path.
- * panel_cols: 0 = whole rows per warp; >0 = process the feature dimension in
+ * panel_cols: -1 = whole rows per warp with the gathered rows staged in shared memory by
+ * cp.async.bulk (TMA) copies into a per-warp ring (deepest memory-level parallelism; F <= 1024);
+ * 0 = whole rows per warp gathered straight into registers; >0 = process the feature dimension in
  * column panels of that many floats, panel-major over the grid, so that one
  * panel of B (n_cols*panel_cols*4 bytes) stays L2-resident while it is gathered.
  * workspace: gcg_plan_workspace_bytes(plan, ldc) bytes (may be NULL if 0). */
@@ -152,6 +154,12 @@ int64_t gcg_colsum_workspace_bytes(int64_t n_rows, int64_t F);
 int gcg_act_bwd_f32(const float* dA, int64_t ld_da, const float* A, int64_t ld_a,
                     float* dP, int64_t ld_dp, int64_t n_rows, int64_t F, int act,
                     void* stream);
+
+/* Stand-alone highway mix O = g*Hc + (1-g)*Hin (O may alias Hc).  Normally fused into the SpMM
+ * epilogue; used where the mix cannot be fused (feature-partitioned multi-GPU propagation). */
+int gcg_highway_fwd_f32(const float* Hc, int64_t ld_hc, const float* g, int64_t ld_g,
+                        const float* Hin, int64_t ld_hin, float* O, int64_t ld_o, int64_t n_rows,
+                        int64_t F, void* stream);
 
 /* Backward of the highway mix  O = g*Hc + (1-g)*Hin,  Hc = act(P):
  *   dP    = g*dO * act'(Hc)          dGpre = dO*(Hc-Hin) * g*(1-g)

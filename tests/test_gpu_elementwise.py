@@ -49,6 +49,16 @@ def test_highway_bwd():
     assert_close(dH.cpu().numpy(), (1 - g) * dO)
 
 
+def test_highway_mix_standalone_equals_fused_formula():
+    from graphconvgeo_b200 import ops
+    rng = np.random.RandomState(7)
+    n, F = 123, 77
+    hc, g, h = (rng.standard_normal((n, F)).astype(np.float32) for _ in range(3))
+    g = np.abs(g) % 1
+    got = ops.highway_mix(to_dev(hc), to_dev(g), to_dev(h)).cpu().numpy()
+    assert np.array_equal(got, g * hc + (np.float32(1) - g) * h)
+
+
 @pytest.mark.parametrize("n,C", [(1, 2), (33, 7), (500, 128), (300, 930), (64, 1024), (10, 2000)])
 def test_softmax_ce_head(n, C):
     from graphconvgeo_b200 import ops

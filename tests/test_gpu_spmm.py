@@ -21,7 +21,7 @@ def run_spmm(A, B, thr=256, **kw):
 
 
 @pytest.mark.parametrize("F", [1, 3, 4, 16, 20, 64, 100, 128, 256, 300, 600, 930, 1024])
-@pytest.mark.parametrize("panel", [0, 16, 64])
+@pytest.mark.parametrize("panel", [-1, 0, 16, 64])
 def test_bit_exact_vs_scipy(F, panel):
     rng = np.random.RandomState(F + panel)
     A = random_csr(rng, 700, 500, 9)
@@ -31,7 +31,7 @@ def test_bit_exact_vs_scipy(F, panel):
     assert np.array_equal(got, ref), "max diff %g" % np.abs(got - ref).max()
 
 
-@pytest.mark.parametrize("panel", [0, 16, 32, 128, 512])
+@pytest.mark.parametrize("panel", [-1, 0, 16, 32, 128, 512])
 def test_hub_rows_are_split_deterministically(panel):
     rng = np.random.RandomState(1)
     A = random_csr(rng, 400, 5000, 6, hub_rows=(0, 17, 399), hub_deg=3000)
@@ -94,6 +94,8 @@ def test_fused_highway_gate_epilogue():
     assert_close(got, ref, atol=2e-6)
     got2, _ = run_spmm(A, B, thr=64, bias=to_dev(b), act="rectify", gate=to_dev(g), carry=to_dev(h))
     assert np.array_equal(got, got2)            # eval mode: same result, H' never written
+    got3, _ = run_spmm(A, B, thr=64, bias=to_dev(b), act="rectify", gate=to_dev(g), carry=to_dev(h), panel_cols=-1)
+    assert np.array_equal(got, got3)            # bulk-copy staged variant: same bits
 
 
 def test_accumulate_mode():
@@ -158,7 +160,7 @@ def test_property_random_shapes():
 
     @settings(max_examples=25, deadline=None)
     @given(st.integers(1, 300), st.integers(1, 300), st.integers(1, 160), st.integers(0, 12),
-           st.sampled_from([0, 16, 32, 64]), st.integers(0, 2 ** 31 - 1))
+           st.sampled_from([-1, 0, 16, 32, 64]), st.integers(0, 2 ** 31 - 1))
     def prop(n, k, F, deg, panel, seed):
         rng = np.random.RandomState(seed)
         A = random_csr(rng, n, k, deg, hub_rows=(0,), hub_deg=min(k, 70))
@@ -196,5 +198,6 @@ def test_full_size_properties_twitter_world_shape():
     s1 = (y.double() * ax.double()).sum().item()
     s2 = (x.double() * ay.double()).sum().item()
     assert abs(s1 - s2) <= 1e-6 * max(abs(s1), 1.0), (s1, s2)
-    # panel-major execution gives the same bits as whole-row execution
+    # panel-major execution and the bulk-copy staged kernel give the same bits as whole-row execution
     assert torch.equal(ops.spmm(Ad, x, panel_cols=16), ax)
+    assert torch.equal(ops.spmm(Ad, x, panel_cols=-1), ops.spmm(Ad, x, panel_cols=0))
