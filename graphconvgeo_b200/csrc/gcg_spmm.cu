@@ -122,11 +122,12 @@ __device__ __forceinline__ void epilogue_store(const SpmmArgs& a, int64_t row, i
   stg_f4_stream(reinterpret_cast<float4*>(cp), v, strm);
 }
 
-template <int G, int VPL>
-__global__ void __launch_bounds__(256) spmm_vec_kernel(const SpmmArgs a) {
+// U = gathered rows in flight per group, MINB = resident CTAs per SM the register budget must allow
+// defaults from the B200 sweep (profiles/r01_spmm_notes.md): no spills, most bytes in flight per SM
+template <int G, int VPL, int U = ((VPL >= 2) ? 2 : 4), int MINB = ((VPL >= 3) ? 2 : 4)>
+__global__ void __launch_bounds__(256, MINB) spmm_vec_kernel(const SpmmArgs a) {
   constexpr int RPW = 32 / G;
   constexpr int RPB = 8 * RPW;
-  constexpr int U = (VPL >= 3) ? 2 : 4;  // gathered rows in flight per group
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int grp = lane / G, s = lane % G;
   const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (grp * G));
@@ -412,9 +413,16 @@ static cudaError_t launch_tma(const SpmmArgs& a, int rows_per_warp, int ring, in
   return cudaGetLastError();
 }
 
+static int g_tune_u = 0, g_tune_minb = 0;   // experiment knobs (gcg_spmm_set_tuning); 0 = defaults
+
 template <int G, int VPL>
 static cudaError_t launch_vec(const SpmmArgs& a, cudaStream_t st) {
   const int64_t grid = (int64_t)a.n_panels * (a.seg_blocks + a.row_blocks);
+  if (G == 32 && g_tune_u > 0) {
+#define GCG_TUNE(UU, MB) if (g_tune_u == UU && g_tune_minb == MB) { spmm_vec_kernel<32, VPL, UU, MB><<<(unsigned)grid, 256, 0, st>>>(a); return cudaGetLastError(); }
+    GCG_TUNE(2, 2) GCG_TUNE(2, 3) GCG_TUNE(3, 2) GCG_TUNE(3, 3) GCG_TUNE(4, 2) GCG_TUNE(4, 3) GCG_TUNE(6, 2) GCG_TUNE(1, 4) GCG_TUNE(2, 4)
+#undef GCG_TUNE
+  }
   spmm_vec_kernel<G, VPL><<<(unsigned)grid, 256, 0, st>>>(a);
   return cudaGetLastError();
 }
@@ -422,6 +430,8 @@ static cudaError_t launch_vec(const SpmmArgs& a, cudaStream_t st) {
 }  // namespace gcg
 
 using namespace gcg;
+
+extern "C" void gcg_spmm_set_tuning(int u, int minb) { gcg::g_tune_u = u; gcg::g_tune_minb = minb; }
 
 extern "C" int gcg_plan_create_csr(int64_t n_rows, int64_t n_cols, int64_t nnz,
                                    const int32_t* d_indptr, const int32_t* d_indices,

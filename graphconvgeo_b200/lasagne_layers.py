@@ -335,13 +335,64 @@ class ConvolutionDenseLayer(_ConvBase):
     ``target_indices`` are propagated (A_hat[idx,:].Z), which equals gathering afterwards.
     kwargs: ``target_indices`` (array or TargetIndices; None keeps every row),
     ``logits=True`` returns the pre-softmax rows (the training step feeds them to the
-    fused softmax/CE head)."""
+    fused softmax/CE head).
+
+    ``propagate_first`` (ctor; "auto" = when num_units > num_inputs, e.g. 1024 regions from 600
+    hidden units): evaluates (H.input).W instead of H.(input.W) -- the same product by
+    associativity, but the sparse propagation then runs at the narrower width (and only for the
+    target rows), which is the cheaper side of this HBM-bound layer.  Results differ from the
+    reference order only by float32 rounding (tests/test_gpu_layers.py)."""
+
+    def __init__(self, incoming, H=None, propagate_first="auto", **kwargs):
+        super().__init__(incoming, H=H, **kwargs)
+        self.propagate_first = (self.num_units > self.num_inputs) if propagate_first == "auto" else bool(propagate_first)
+
+    def _forward_propagate_first(self, input, ti, kwargs):
+        N = input.shape[0]
+        Hm = self.H if ti is None else ti.Hsub
+        n_out = N if ti is None else ti.n
+        q = ops.spmm(Hm, input, out=self._mat(("Q", n_out), n_out, self.num_inputs))      # H[idx,:].input
+        self._q = q
+        fused_act = "identity" if self.nonlinearity == "softmax" else self.nonlinearity
+        out = ops.gemm(q, self.W, bias=self.b, act=fused_act,
+                       out=self._mat(("out", n_out), n_out, self.num_units))               # (.).W + b
+        self._out = out
+        if self.nonlinearity == "softmax" and not kwargs.get("logits", False):
+            probs = self._mat(("probs", n_out), n_out, self.num_units)
+            ops.softmax_ce(out, probs=probs)
+            return probs
+        return out
+
+    def _backward_propagate_first(self, grad_output, preact, input_mask, need_input_grad):
+        ti = self._ti
+        N = self._in.shape[0]
+        if self.nonlinearity in ("softmax", "identity") or preact:
+            dPr = grad_output
+        else:
+            dPr = ops.act_bwd(grad_output, self._out, self.nonlinearity, out=self._mat("dPr", *grad_output.shape))
+        if self.b is not None:
+            ops.colsum(dPr, out=self._grad("b", self.b))
+        ops.gemm(self._q, dPr, transA=True, out=self._grad("W", self.W))                   # dW = Q^T.dP
+        if not need_input_grad:
+            return None
+        dQ = ops.gemm(dPr, self.W, transB=True, out=self._mat(("dQ", dPr.shape[0]), dPr.shape[0], self.num_inputs))
+        if ti is not None:
+            ptr, pos = ti.positions
+            S = ops.scatter_rows(dQ, ptr, pos, N, out=self._operand("dP", N, self.num_inputs))
+        else:
+            S = dQ
+        dIn = ops.spmm(self.H, S, out=self._mat("dIn", N, self.num_inputs))                # H^T = H
+        if input_mask is not None:
+            ops.act_bwd(dIn, input_mask[0], input_mask[1], out=dIn)
+        return dIn
 
     def get_output_for(self, input, **kwargs):
         ti = self._target(kwargs.get("target_indices"))                    # :81
         N = input.shape[0]
         self._in = input
         self._ti = ti
+        if self.propagate_first:
+            return self._forward_propagate_first(input, ti, kwargs)
         z = ops.gemm(input, self.W, out=self._operand("Z", N, self.num_units))   # :82
         Hm = self.H if ti is None else ti.Hsub
         n_out = N if ti is None else ti.n
@@ -359,6 +410,8 @@ class ConvolutionDenseLayer(_ConvBase):
         """``grad_output``: grad wrt the layer output rows (wrt the LOGITS for a softmax
         layer -- the head produces it fused with the loss).  ``input_mask=(A_prev, act)``
         fuses the previous layer's act' into the dH product."""
+        if self.propagate_first:
+            return self._backward_propagate_first(grad_output, preact, input_mask, need_input_grad)
         ti = self._ti
         N = self._in.shape[0]
         if self.nonlinearity in ("softmax", "identity") or preact:
@@ -390,6 +443,7 @@ class HighwayConvolutionDenseLayer(ConvolutionDenseLayer):
 
     def __init__(self, incoming, H=None, Wg=None, bg=Constant(0.0), rng=None, **kwargs):
         super().__init__(incoming, H=H, rng=rng, **kwargs)
+        self.propagate_first = False
         assert self.num_inputs == self.num_units, "highway gate needs in-dim == out-dim"
         assert self.nonlinearity != "softmax"
         Wg = GlorotUniform() if Wg is None else Wg

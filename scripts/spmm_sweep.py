@@ -58,6 +58,7 @@ def main():
     ap.add_argument("--panel", type=int, nargs="+", default=[0])
     ap.add_argument("--reorder", nargs="+", default=["none"])
     ap.add_argument("--thr", type=int, default=256)
+    ap.add_argument("--tune", nargs="+", default=["0,0"], help="u,minb pairs for gcg_spmm_set_tuning")
     args = ap.parse_args()
     dev = torch.device("cuda")
     peak = 6550.4
@@ -93,8 +94,12 @@ def main():
                         out = ops.alloc_mat(n, F, dev)
                         alg = 8 * A.nnz + 4 * (n + 1) + 8 * n * F
                         for panel in args.panel:
+                          for tune in args.tune:
+                            tu, tm = (int(x) for x in tune.split(","))
+                            _lib.lib().gcg_spmm_set_tuning(tu, tm)
                             mean, mn = timeit(lambda: ops.spmm(A, Bm, out=out, panel_cols=panel))
-                            print(json.dumps({"n": n, "deg": deg, "graph": kind, "reorder": ro, "F": F, "panel": panel,
+                            _lib.lib().gcg_spmm_set_tuning(0, 0)
+                            print(json.dumps({"tune": tune, "n": n, "deg": deg, "graph": kind, "reorder": ro, "F": F, "panel": panel,
                                               "nnz": A.nnz, "max_deg": info["max_degree"], "n_long": info["n_long_rows"],
                                               "ms": round(mean, 4), "ms_min": round(mn, 4),
                                               "alg_GBps": round(alg / mean / 1e6, 1), "frac_of_measured_peak": round(alg / mean / 1e6 / peak, 4),

@@ -140,3 +140,36 @@ def test_get_output_and_param_helpers():
     assert torch.all(l1.b == 1.0)
     with pytest.raises(ValueError, match="mismatch"):
         L.set_all_param_values(l2, vals[:-1])
+
+
+@pytest.mark.parametrize("act", ["softmax", "rectify"])
+def test_propagate_first_association_matches_reference_order(act):
+    """(H.input).W == H.(input.W) up to float32 rounding, forward and backward (num_units > num_inputs)."""
+    from graphconvgeo_b200 import lasagne_layers as L
+    rng, X, A = problem(6)
+    n, fin, fout = X.shape[0], 24, 40
+    Hin = (rng.standard_normal((n, fin)) * 0.3).astype(np.float32)
+    W = go.glorot_uniform(rng, fin, fout)
+    b = (rng.standard_normal(fout) * 0.1).astype(np.float32)
+    idx = rng.choice(n, size=150, replace=True).astype(np.int32)
+    outs, grads_w, grads_b, grads_in = [], [], [], []
+    dO = (rng.standard_normal((150, fout)) * 0.1).astype(np.float32)
+    prev = np.maximum(rng.standard_normal((n, fin)), 0).astype(np.float32)
+    for pf in (False, True):
+        ly = L.ConvolutionDenseLayer(L.InputLayer((None, fin)), H=A, num_units=fout, W=W, b=b, nonlinearity=act,
+                                     propagate_first=pf)
+        assert ly.propagate_first == pf
+        out = ly.get_output_for(to_dev(Hin), target_indices=idx, logits=True)
+        outs.append(out.cpu().numpy().copy())
+        dIn = ly.backward(to_dev(dO), input_mask=(to_dev(prev), "rectify"))
+        grads_w.append(ly.grads["W"].cpu().numpy().copy())
+        grads_b.append(ly.grads["b"].cpu().numpy().copy())
+        grads_in.append(dIn.cpu().numpy().copy())
+    ref = go.convolution_dense(Hin, W, b, A, idx, "identity" if act == "softmax" else act)
+    for o in outs:
+        assert_close(o, ref, atol=2e-6)
+    assert_close(grads_w[1], grads_w[0], atol=2e-6)
+    assert_close(grads_b[1], grads_b[0], atol=2e-6)
+    assert_close(grads_in[1], grads_in[0], atol=2e-6)
+    auto = L.ConvolutionDenseLayer(L.InputLayer((None, fin)), H=A, num_units=fout)
+    assert auto.propagate_first and not L.ConvolutionDenseLayer(L.InputLayer((None, fout)), H=A, num_units=fin).propagate_first

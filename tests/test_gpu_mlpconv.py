@@ -239,3 +239,25 @@ def test_training_step_with_tensor_core_gemms(n_layers, highway):
                 g = g + np.float32(0.5e-6) * (np.sign(params[k]) + np.float32(2) * params[k])
             assert_close(g, grads[k], atol=4e-6, what="grad %d (%s)" % (k, name))
             k += 1
+
+
+def test_model_with_more_regions_than_hidden_units_uses_propagate_first():
+    """Twitter-World shape in miniature: C > hidden, so the output layer propagates first."""
+    w = workload(bucket=4, hidden=24)
+    assert w.n_classes > w.hidden
+    rng = np.random.RandomState(8)
+    params = go.init_params(rng, w.X.shape[1], w.hidden, w.n_classes, 3, True)
+    idx = rng.choice(w.train_indices, size=400).astype(np.int32)
+    y = w.Y[idx].astype(np.int32)
+    net = go.GCNOracle(w.X, w.A_hat, 3, True, (1e-4, 2e-4))
+    loss, acc, grads, cache = net.loss_and_grads(params, idx, y)
+    m = make_model(w, 3, True, params, idx)
+    assert m.l_out.propagate_first
+    m.f_train()
+    l_gpu, a_gpu = m.train_results()
+    assert abs(l_gpu - float(loss)) <= 1e-5 * abs(float(loss))
+    assert_close(m.l_out._out.cpu().numpy(), cache["logits"], atol=2e-6, what="logits")
+    st = go.AdamState(params)
+    go.adam_step(params, grads, st)
+    for p_gpu, p in zip(m.get_param_values(), params):
+        assert_close(p_gpu, p, atol=2e-6, what="params after step")
