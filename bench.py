@@ -240,7 +240,7 @@ def run_gpu(args):
     launches = ops.launch_count(reset=True)
     m._graph = m_graph
 
-    breakdown = op_breakdown(m, dev) if (args.breakdown and world == 1) else None
+    breakdown = op_breakdown(m, dev) if args.breakdown else None       # collective-safe: every rank runs it
 
     # ---------------- e2e: host inputs re-uploaded every epoch, loss/acc read back
     e2e = None
@@ -338,9 +338,10 @@ def op_breakdown(m, dev):
         a[1] += s.elapsed_time(e)
     total = s0.elapsed_time(e0)
     rows = sorted(agg.items(), key=lambda kv: -kv[1][1])
-    log("---- op breakdown of one eager epoch: %.2f ms total ----" % total)
-    for tag, (c, t) in rows:
-        log("  %-70s x%-2d %8.3f ms  %5.1f%%" % (tag, c, t, 100 * t / total))
+    if int(os.environ.get("RANK", "0")) == 0:
+        log("---- op breakdown of one eager epoch: %.2f ms total ----" % total)
+        for tag, (c, t) in rows:
+            log("  %-70s x%-2d %8.3f ms  %5.1f%%" % (tag, c, t, 100 * t / total))
     return {"epoch_ms_eager": total, "ops": [{"op": tag, "calls": c, "ms": t} for tag, (c, t) in rows]}
 
 

@@ -53,6 +53,8 @@ PROTOTYPES = {
     "gcg_sum_f32": (c_int, [c_vp, c_i64, c_f32, c_vp, c_vp]),
     "gcg_scatter_rows_f32": (c_int, [c_vp, c_i64, c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp]),
     "gcg_gather_rows_f32": (c_int, [c_vp, c_i64, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp]),
+    "gcg_pack_cols_f32": (c_int, [c_vp, c_i64, c_i64, c_i64, c_i32, c_i64, c_vp, c_vp]),
+    "gcg_unpack_cols_f32": (c_int, [c_vp, c_i64, c_i64, c_i32, c_i64, c_vp, c_i64, c_vp]),
     "gcg_adam_step_f32": (c_int, [c_i32, C.POINTER(c_vp), C.POINTER(c_vp), C.POINTER(c_vp), C.POINTER(c_vp),
                                   C.POINTER(c_i64), C.POINTER(c_f32), c_f32, c_f32, c_f32, c_f32, c_vp, c_vp,
                                   c_vp, c_i64, c_vp]),

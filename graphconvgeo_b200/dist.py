@@ -217,11 +217,7 @@ class FeatureSplitCSRMatrix:
             out = ops.alloc_mat(my_rows, F, B.device)
         # 1. row layout -> column slices (zero padded), one all-to-all
         send = self._buf("send", (P, n_loc, Fp))
-        for q in range(P):
-            c0 = q * Fp
-            w = max(0, min(Fp, F - c0))
-            if w > 0:
-                send[q, :, :w].copy_(B[:, c0:c0 + w])
+        ops.pack_cols(B, P, Fp, send)
         recv = self._buf("recv", (P * n_loc, Fp))
         dist.all_to_all_single(recv.view(-1), send.view(-1), group=part.group)
         part.bytes_gathered += (P - 1) * n_loc * Fp * 4
@@ -241,13 +237,8 @@ class FeatureSplitCSRMatrix:
                                input_split_sizes=self.row_counts, group=part.group)
         if my_rows == 0:
             return out
-        back3 = back[:P * my_rows].view(P, my_rows, Fp)
         dst = out if gate is None or conv_out is None else conv_out
-        for q in range(P):
-            c0 = q * Fp
-            w = max(0, min(Fp, F - c0))
-            if w > 0:
-                dst[:, c0:c0 + w].copy_(back3[q, :, :w])
+        ops.unpack_cols(back[:P * my_rows], P, Fp, dst)
         if gate is not None:
             ops.highway_mix(dst, gate, carry, out=out)       # out = g*Hc + (1-g)*H ; Hc kept in conv_out
         return out
@@ -374,15 +365,18 @@ class DistMLPCONV(MLPCONV):
         n, C = logits.shape
         G = self.l_out._mat("G", n, C)
         hb = self._head(logits, y, ti.n_global, grad=G)
-        self._backward(G)
-        works = [dist.all_reduce(g, group=self.group, async_op=True) for g in self.grads]
-        works.append(dist.all_reduce(hb["out"], group=self.group, async_op=True))
+        works = [dist.all_reduce(hb["out"], group=self.group, async_op=True)]
+        self._backward(G, works)          # each layer's gradient all-reduce starts as soon as it is computed
         for w in works:
             w.wait()
         self.adam.step()
         self._train_hb = hb
 
-    def _backward(self, G):
+    def _backward(self, G, works=None):
+        def reduce_grads(ly):
+            if works is not None:
+                for g in ly.grads.values():
+                    works.append(dist.all_reduce(g, group=self.group, async_op=True))
         grad, preact = G, False
         for i in range(len(self.layers) - 1, -1, -1):
             ly = self.layers[i]
@@ -393,11 +387,13 @@ class DistMLPCONV(MLPCONV):
                 mask = (prev._out, prev.nonlinearity)
             if isinstance(ly, L.SparseConvolutionDenseLayer):
                 ly.backward(grad, preact=preact)
+                reduce_grads(ly)
                 break
             if isinstance(ly, L.HighwayConvolutionDenseLayer):
                 grad = ly.backward(grad, input_mask=mask)
             else:
                 grad = ly.backward(grad, preact=preact, input_mask=mask)
+            reduce_grads(ly)
             preact = mask is not None
 
     def f_train(self):

@@ -284,6 +284,22 @@ def gather_rows(X, idx, out=None):
     return out
 
 
+def pack_cols(src, P, Fp, dst):
+    """[n, F] -> [P, n, Fp] column slices, zero padded (gcg_pack_cols_f32)."""
+    sp, ld = _mat(src, "src")
+    _lib.check(_lib.lib().gcg_pack_cols_f32(sp, ld, src.shape[0], src.shape[1], int(P), int(Fp),
+                                            C.c_void_p(dst.data_ptr()), _stream()), "gcg_pack_cols_f32")
+    return dst
+
+
+def unpack_cols(src, P, Fp, dst):
+    """[P, n, Fp] column slices -> [n, F] (gcg_unpack_cols_f32)."""
+    dp, ld = _mat(dst, "dst")
+    _lib.check(_lib.lib().gcg_unpack_cols_f32(C.c_void_p(src.data_ptr()), dst.shape[0], dst.shape[1], int(P), int(Fp),
+                                              dp, ld, _stream()), "gcg_unpack_cols_f32")
+    return dst
+
+
 def scatter_positions(idx, n_rows, device):
     """CSR-like inverse of ``target_indices``: for node r the positions i with
     idx[i] == r, ascending (host, once per index vector)."""

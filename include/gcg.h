@@ -195,6 +195,14 @@ int gcg_scatter_rows_f32(const float* G, int64_t ld_g, const int32_t* pos_ptr,
 int gcg_gather_rows_f32(const float* X, int64_t ld_x, const int32_t* idx, int64_t n_idx,
                         int64_t C, float* out, int64_t ld_out, void* stream);
 
+/* Transposes around the feature-sliced multi-GPU propagation (graphconvgeo_b200/dist.py):
+ * pack:   src [n_rows, F] (ld)  ->  dst [P][n_rows][Fp], slice q = columns [q*Fp, (q+1)*Fp), zero padded;
+ * unpack: the inverse (pad columns dropped).  Fp and ld multiples of 4, 16-byte aligned operands. */
+int gcg_pack_cols_f32(const float* src, int64_t ld, int64_t n_rows, int64_t F, int32_t P, int64_t Fp,
+                      float* dst, void* stream);
+int gcg_unpack_cols_f32(const float* src, int64_t n_rows, int64_t F, int32_t P, int64_t Fp, float* dst,
+                        int64_t ld, void* stream);
+
 /* ---------------------------------------------------------------- optimiser */
 
 /* One fused multi-tensor step of lasagne.updates.adam (mlpconv.py:263) with the

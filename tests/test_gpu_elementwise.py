@@ -138,3 +138,21 @@ def test_adam_matches_lasagne_adam_oracle():
         for p_d, p in zip(pd, P):
             assert_close(p_d.cpu().numpy(), p, atol=1e-6, what="step %d" % step)
     assert adam.t[0].item() == 4.0
+
+
+@pytest.mark.parametrize("n,F,P", [(5, 7, 2), (1000, 600, 8), (333, 1024, 8), (64, 30, 4)])
+def test_pack_unpack_column_slices(n, F, P):
+    from graphconvgeo_b200 import ops
+    rng = np.random.RandomState(n + F)
+    X = rng.standard_normal((n, F)).astype(np.float32)
+    Fp = (-(-F // P) + 3) // 4 * 4
+    dst = torch.full((P, n, Fp), 7.0, device="cuda")
+    ops.pack_cols(to_dev(X), P, Fp, dst)
+    ref = np.zeros((P, n, Fp), np.float32)
+    for q in range(P):
+        w = max(0, min(Fp, F - q * Fp))
+        ref[q, :, :w] = X[:, q * Fp:q * Fp + w]
+    assert np.array_equal(dst.cpu().numpy(), ref)
+    back = ops.alloc_mat(n, F, "cuda")
+    ops.unpack_cols(dst, P, Fp, back)
+    assert np.array_equal(back.cpu().numpy(), X)

@@ -20,7 +20,7 @@ def run_spmm(A, B, thr=256, **kw):
     return out.cpu().numpy(), Ad
 
 
-@pytest.mark.parametrize("F", [1, 3, 4, 16, 20, 64, 100, 128, 256, 300, 600, 930, 1024])
+@pytest.mark.parametrize("F", [1, 3, 4, 16, 20, 64, 76, 100, 128, 256, 300, 600, 930, 1024])
 @pytest.mark.parametrize("panel", [-1, 0, 16, 64])
 def test_bit_exact_vs_scipy(F, panel):
     rng = np.random.RandomState(F + panel)
