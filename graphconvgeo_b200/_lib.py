@@ -64,6 +64,11 @@ PROTOTYPES = {
     "gcg_kdtree_fit_host": (c_int, [c_vp, c_i64, c_i32, c_i64, c_vp, C.POINTER(c_i64)]),
     "gcg_ahat_nnz_host": (c_i64, [c_i64, c_vp, c_vp]),
     "gcg_ahat_build_host": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "gcg_ahat_device_workspace_bytes": (c_i64, [c_i64]),
+    "gcg_ahat_indptr_device": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
+    "gcg_ahat_fill_device": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
+    "gcg_haversine_nearest_f64": (c_int, [c_vp, c_i64, c_vp, c_i32, c_vp, c_vp, c_vp]),
+    "gcg_haversine_pairs_f64": (c_int, [c_vp, c_vp, c_i64, c_vp, c_vp]),
     "gcg_csr_transpose_host": (c_int, [c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "gcg_csr_gather_rows_host": (c_i64, [c_i64, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
     "gcg_csr_permute_host": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),

@@ -623,15 +623,12 @@ extern "C" int gcg_spmm_csr_f32(const gcg_plan* p, const float* B, int64_t ldb, 
   // choose (G, VPL): panel width in float4 = G*VPL
   int want_f4 = a.f4_total;
   if (panel_cols > 0) want_f4 = (int)std::min<int64_t>(a.f4_total, std::max<int64_t>(1, (panel_cols + 3) / 4));
-  // (G lanes per row, VPL float4 per lane): the narrowest group that covers the panel, so that
-  // several rows share a warp when F is small (feature-sliced multi-GPU operands are F/P wide)
+  // (G lanes per row, VPL float4 per lane): the narrowest power-of-two group that covers the panel
   int G, VPL;
   if (want_f4 <= 4) { G = 4; VPL = 1; }
   else if (want_f4 <= 8) { G = 8; VPL = 1; }
   else if (want_f4 <= 16) { G = 16; VPL = 1; }
-  else if (want_f4 <= 24) { G = 8; VPL = 3; }
-  else if (want_f4 <= 32) { G = 16; VPL = 2; }
-  else { G = 32; VPL = (int)std::min<int64_t>(5, ceil_div(want_f4, 32)); }
+  else { G = 32; VPL = (int)std::min<int64_t>(5, ceil_div(want_f4, 32)); }   // (8,3)/(16,2) groups measured slower than (32,1) at f4 = 19
   a.panel_f4 = G * VPL;
   a.n_panels = (int)ceil_div(a.f4_total, a.panel_f4);
   const int rpb = 8 * (32 / G);
@@ -643,9 +640,7 @@ extern "C" int gcg_spmm_csr_f32(const gcg_plan* p, const float* B, int64_t ldb, 
   switch (G * 8 + VPL) {
     case 4 * 8 + 1: e = launch_vec<4, 1>(a, st); break;
     case 8 * 8 + 1: e = launch_vec<8, 1>(a, st); break;
-    case 8 * 8 + 3: e = launch_vec<8, 3>(a, st); break;
     case 16 * 8 + 1: e = launch_vec<16, 1>(a, st); break;
-    case 16 * 8 + 2: e = launch_vec<16, 2>(a, st); break;
     case 32 * 8 + 1: e = launch_vec<32, 1>(a, st); break;
     case 32 * 8 + 2: e = launch_vec<32, 2>(a, st); break;
     case 32 * 8 + 3: e = launch_vec<32, 3>(a, st); break;

@@ -211,3 +211,23 @@ def build_ahat_host(adj):
     _lib.check(L.gcg_ahat_build_host(n, _np_ptr(ip), _np_ptr(ix), _np_ptr(w) if w is not None else None,
                                      _np_ptr(oip), _np_ptr(oix), _np_ptr(ov)), "gcg_ahat_build_host")
     return sp.csr_matrix((ov, oix, oip), shape=(n, n))
+
+
+def build_ahat_device(indptr, indices, n):
+    """Device-side A_hat (tensormain.py:170-180,221) from a binary adjacency pattern already on the GPU
+    (int32 CSR, sorted columns).  Bit-identical to build_ahat_host; returns a CSRMatrix."""
+    dev = indptr.device
+    L = _lib.lib()
+    stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    wsb = int(L.gcg_ahat_device_workspace_bytes(n))
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    out_ip = torch.empty(n + 1, dtype=torch.int32, device=dev)
+    total = torch.zeros(1, dtype=torch.int32, device=dev)
+    _lib.check(L.gcg_ahat_indptr_device(n, indptr.data_ptr(), indices.data_ptr(), out_ip.data_ptr(), total.data_ptr(),
+                                        ws.data_ptr(), wsb, stream), "gcg_ahat_indptr_device")
+    nnz = int(indices.numel()) + int(total.item())
+    out_ix = torch.empty(nnz, dtype=torch.int32, device=dev)
+    out_v = torch.empty(nnz, dtype=torch.float32, device=dev)
+    _lib.check(L.gcg_ahat_fill_device(n, indptr.data_ptr(), indices.data_ptr(), out_ip.data_ptr(), out_ix.data_ptr(),
+                                      out_v.data_ptr(), ws.data_ptr(), wsb, stream), "gcg_ahat_fill_device")
+    return CSRMatrix(out_ip, out_ix, out_v, (n, n))

@@ -290,14 +290,20 @@ def make_workload_device(name="twitter-world", device="cuda", seed=77, community
     locs, city = city_locations(n, cfg["n_cities"], seed)
     city_t = torch.from_numpy(city).to(dev) if community else None
     ip, ix = _torch_graph(n, cfg["avg_deg"], gen, dev, city=city_t)
-    # A_hat through the product's host builder (gcg_ahat_build_host): float64 normalise, cast
-    hip, hix = ip.cpu().numpy(), ix.cpu().numpy()
-    L = _lib.lib()
-    nnz = L.gcg_ahat_nnz_host(n, _np_ptr(hip), _np_ptr(hix))
-    oip, oix, ov = np.empty(n + 1, np.int32), np.empty(nnz, np.int32), np.empty(nnz, np.float32)
-    _lib.check(L.gcg_ahat_build_host(n, _np_ptr(hip), _np_ptr(hix), None, _np_ptr(oip), _np_ptr(oix), _np_ptr(ov)),
-               "gcg_ahat_build_host")
-    a_hat = CSRMatrix.from_host((oip, oix, ov), (n, n), dev)
+    if dev.type == "cuda":
+        # A_hat through the product's device builder (gcg_ahat_*_device): float64 normalise, cast
+        from .sparse import build_ahat_device
+        a_hat = build_ahat_device(ip, ix, n)
+        oip = a_hat.indptr.cpu().numpy()
+    else:
+        # A_hat through the product's host builder (gcg_ahat_build_host)
+        hip, hix = ip.cpu().numpy(), ix.cpu().numpy()
+        L = _lib.lib()
+        nnz = L.gcg_ahat_nnz_host(n, _np_ptr(hip), _np_ptr(hix))
+        oip, oix, ov = np.empty(n + 1, np.int32), np.empty(nnz, np.int32), np.empty(nnz, np.float32)
+        _lib.check(L.gcg_ahat_build_host(n, _np_ptr(hip), _np_ptr(hix), None, _np_ptr(oip), _np_ptr(oix), _np_ptr(ov)),
+                   "gcg_ahat_build_host")
+        a_hat = CSRMatrix.from_host((oip, oix, ov), (n, n), dev)
     del ip, ix
     xip, xix, xv = _torch_tfidf(n, cfg["vocab"], cfg["terms"], gen, dev)
     X = CSRMatrix(xip, xix, xv, (n, cfg["vocab"]), long_row_threshold=1024)

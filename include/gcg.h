@@ -246,6 +246,27 @@ int gcg_ahat_build_host(int64_t n, const int32_t* h_indptr, const int32_t* h_ind
                         const double* h_weights, int32_t* out_indptr, int32_t* out_indices,
                         float* out_vals);
 
+/* Device version of the two calls above for a BINARY adjacency pattern that is already a device CSR
+ * (sorted columns): phase 1 writes out_indptr[n+1] and the output nnz (*d_total, device int32);
+ * phase 2 writes the column indices (unit diagonal inserted) and the float32 values.  Bit-identical
+ * to gcg_ahat_build_host.  workspace >= gcg_ahat_device_workspace_bytes(n), the same buffer for both. */
+int64_t gcg_ahat_device_workspace_bytes(int64_t n);
+int gcg_ahat_indptr_device(int64_t n, const int32_t* d_indptr, const int32_t* d_indices,
+                           int32_t* out_indptr, int32_t* d_total, void* workspace,
+                           int64_t workspace_bytes, void* stream);
+int gcg_ahat_fill_device(int64_t n, const int32_t* d_indptr, const int32_t* d_indices,
+                         const int32_t* out_indptr, int32_t* out_indices, float* out_vals,
+                         void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Label pipeline around the hot path, float64 haversine (R = 6371.0088 km):
+ *  nearest: out_idx[i] = argmin_c haversine(points[i], medians[c]) (first minimum) -- the brute-force
+ *           1-NN that assigns dev/test users to regions, data.py:416-419; out_km optional.
+ *  pairs:   out_km[i] = haversine(a[i], b[i]) -- the per-user error of geo_eval, tensormain.py:38-54.
+ * points / medians / a / b are [n, 2] (lat, lon) float64 device arrays. */
+int gcg_haversine_nearest_f64(const double* d_points, int64_t n, const double* d_medians, int32_t n_medians,
+                              int64_t* d_out_idx, double* d_out_km, void* stream);
+int gcg_haversine_pairs_f64(const double* d_a, const double* d_b, int64_t n, double* d_out_km, void* stream);
+
 /* CSR transpose (stable: rows ascending inside each output row), used once per
  * fit to build X^T for dW1 = X^T.dZ1 (Dot.grad of lasagne_layers.py:26,65). */
 int gcg_csr_transpose_host(int64_t n_rows, int64_t n_cols, const int32_t* h_indptr,

@@ -173,3 +173,24 @@ def test_propagate_first_association_matches_reference_order(act):
     assert_close(grads_in[1], grads_in[0], atol=2e-6)
     auto = L.ConvolutionDenseLayer(L.InputLayer((None, fin)), H=A, num_units=fout)
     assert auto.propagate_first and not L.ConvolutionDenseLayer(L.InputLayer((None, fout)), H=A, num_units=fin).propagate_first
+
+
+@pytest.mark.parametrize("n,deg,seed", [(1, 0, 0), (50, 3, 1), (3000, 8, 2), (20000, 20, 3)])
+def test_device_ahat_builder_is_bit_identical_to_host_and_oracle(n, deg, seed):
+    """A_hat = D^-1/2 (A, unit diagonal) D^-1/2 built on the GPU, float64 then cast."""
+    from graphconvgeo_b200.sparse import build_ahat_device, build_ahat_host
+    from graphconvgeo_b200.synth import powerlaw_graph
+    adj = powerlaw_graph(n, deg, seed) if n > 1 else sp.csr_matrix((1, 1))
+    if n > 100:                                   # some rows that already carry their diagonal
+        adj = sp.csr_matrix(adj + sp.diags((np.arange(n) % 7 == 0).astype(np.float64)))
+        adj.data[:] = 1.0
+    adj.sort_indices()
+    ref = go.build_ahat(adj)
+    host = build_ahat_host(adj)
+    ip = torch.from_numpy(adj.indptr.astype(np.int32)).cuda()
+    ix = torch.from_numpy(adj.indices.astype(np.int32)).cuda()
+    got = build_ahat_device(ip, ix, n)
+    assert np.array_equal(got.indptr.cpu().numpy(), ref.indptr)
+    assert np.array_equal(got.indices.cpu().numpy(), ref.indices)
+    assert np.array_equal(got.data.cpu().numpy(), ref.data)
+    assert np.array_equal(host.data, ref.data)
