@@ -124,8 +124,8 @@ __device__ __forceinline__ void epilogue_store(const SpmmArgs& a, int64_t row, i
 
 // U = gathered rows in flight per group, MINB = resident CTAs per SM the register budget must allow
 // defaults from the B200 sweep (profiles/r01_spmm_notes.md): no spills, most bytes in flight per SM
-template <int G, int VPL, int U = ((VPL >= 2) ? 2 : 4), int MINB = ((VPL >= 3) ? 2 : 4)>
-__global__ void __launch_bounds__(256, MINB) spmm_vec_kernel(const SpmmArgs a) {
+template <int G, int VPL, int U>
+__device__ __forceinline__ void spmm_vec_body(const SpmmArgs& a) {
   constexpr int RPW = 32 / G;
   constexpr int RPB = 8 * RPW;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -220,6 +220,16 @@ __global__ void __launch_bounds__(256, MINB) spmm_vec_kernel(const SpmmArgs a) {
     for (int k = 0; k < VPL; ++k)
       if (cv[k]) epilogue_store(a, row, c_base + k * G, acc[k], strm);
   }
+}
+
+template <int G, int VPL, int U = ((VPL >= 2) ? 2 : 4), int MINB = ((VPL >= 3) ? 2 : 4)>
+__global__ void __launch_bounds__(256, MINB) spmm_vec_kernel(const SpmmArgs a) {
+  spmm_vec_body<G, VPL, U>(a);
+}
+// same body, register budget left to the compiler's own heuristic (no min-blocks hint)
+template <int G, int VPL, int U>
+__global__ void __launch_bounds__(256) spmm_vec_kernel_nb(const SpmmArgs a) {
+  spmm_vec_body<G, VPL, U>(a);
 }
 
 // One warp per long row: sum the segment partials in order, apply the epilogue.
@@ -420,10 +430,15 @@ static cudaError_t launch_vec(const SpmmArgs& a, cudaStream_t st) {
   const int64_t grid = (int64_t)a.n_panels * (a.seg_blocks + a.row_blocks);
   if (G == 32 && g_tune_u > 0) {
 #define GCG_TUNE(UU, MB) if (g_tune_u == UU && g_tune_minb == MB) { spmm_vec_kernel<32, VPL, UU, MB><<<(unsigned)grid, 256, 0, st>>>(a); return cudaGetLastError(); }
-    GCG_TUNE(2, 2) GCG_TUNE(2, 3) GCG_TUNE(3, 2) GCG_TUNE(3, 3) GCG_TUNE(4, 2) GCG_TUNE(4, 3) GCG_TUNE(6, 2) GCG_TUNE(1, 4) GCG_TUNE(2, 4)
+    GCG_TUNE(2, 2) GCG_TUNE(2, 3) GCG_TUNE(3, 2) GCG_TUNE(4, 2) GCG_TUNE(2, 4)
 #undef GCG_TUNE
+    if (g_tune_minb == 0 && g_tune_u == 2) { spmm_vec_kernel_nb<32, VPL, 2><<<(unsigned)grid, 256, 0, st>>>(a); return cudaGetLastError(); }
+    if (g_tune_minb == 0 && g_tune_u == 4) { spmm_vec_kernel_nb<32, VPL, 4><<<(unsigned)grid, 256, 0, st>>>(a); return cudaGetLastError(); }
   }
-  spmm_vec_kernel<G, VPL><<<(unsigned)grid, 256, 0, st>>>(a);
+  // A/B on B200 (profiles/r01_spmm_notes.md): whole 600-wide rows run 14 % faster when the register
+  // budget is left to the compiler (126 regs) than under a (256, 2) bound; F = 256 is fastest at 64 regs
+  if (G == 32 && VPL >= 3) spmm_vec_kernel_nb<32, VPL, 2><<<(unsigned)grid, 256, 0, st>>>(a);
+  else spmm_vec_kernel<G, VPL><<<(unsigned)grid, 256, 0, st>>>(a);
   return cudaGetLastError();
 }
 
