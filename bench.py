@@ -185,7 +185,7 @@ def run_gpu(args):
                         n_layers=args.layers, highway=bool(args.highway), seed=1, device=dev, cuda_graph=True)
     if world > 1:
         from graphconvgeo_b200.dist import DistMLPCONV
-        m = DistMLPCONV(partition=args.partition, **model_kwargs)
+        m = DistMLPCONV(partition=args.partition, peer_memory=not args.no_peer_memory, **model_kwargs)
     else:
         m = MLPCONV(**model_kwargs)
     t0 = time.time()
@@ -267,8 +267,10 @@ def run_gpu(args):
         "config": dict(bench_config(args), nodes=wl.meta["n"], vocab=wl.meta["vocab"], hidden=wl.hidden,
                        regions=wl.n_classes, nnz_A=wl.meta["nnz_A"], nnz_X=wl.meta["nnz_X"],
                        max_degree=wl.meta["max_degree"], graph="community" if wl.meta["community"] else "chung-lu",
-                       parallelism=("rows x%d, A_hat.Z %s" % (world, "feature-sliced + all-to-all" if args.partition == "feature"
-                                                              else "row blocks + all-gather")) if world > 1 else "single GPU",
+                       parallelism=("rows x%d, A_hat.Z %s" % (world, ("feature-sliced, transposes by %s" % (
+                           "peer-memory stores over NVLink" if getattr(getattr(m, "part", None), "peer", None) is not None
+                           else "NCCL all-to-all")) if getattr(m, "partition", "") == "feature" else "row blocks + NCCL all-gather"))
+                       if world > 1 else "single GPU",
                        gemm_mode=os.environ.get("GCG_GEMM_MODE", "auto")),
         "clocks": sampler.summary(), "gpu_launches": launches * args.steps,
         "launches_per_epoch": launches, "loss": loss, "acc": acc,
@@ -428,7 +430,8 @@ def main():
     ap.add_argument("--random-graph", action="store_true", help="Chung-Lu graph without community structure")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--breakdown", action="store_true", help="per-op CUDA-event breakdown of one eager epoch")
-    ap.add_argument("--partition", default="feature", choices=["feature", "row"],
+    ap.add_argument("--no-peer-memory", action="store_true", help="feature mode: NCCL all-to-all instead of P2P stores")
+    ap.add_argument("--partition", default="auto", choices=["auto", "feature", "row"],
                     help="multi-GPU scheme for A_hat.Z: feature slices + all-to-all, or row blocks + all-gather")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -76,8 +76,9 @@ PROTOTYPES = {
     "gcg_peer_free": (c_int, [c_vp]),
     "gcg_peer_open": (c_int, [c_vp, C.POINTER(c_vp)]),
     "gcg_peer_close": (c_int, [c_vp]),
-    "gcg_allgather_rows_f32": (c_int, [C.POINTER(c_vp), c_int, c_int, C.POINTER(c_i64), c_i64, c_i64, c_vp,
-                                       c_i64, c_vp]),
+    "gcg_push_cols_f32": (c_int, [c_vp, c_i64, c_i64, c_i64, c_i32, c_i64, C.POINTER(c_vp), c_i64, c_vp]),
+    "gcg_push_rows_f32": (c_int, [c_vp, C.POINTER(c_i64), c_i32, c_i64, C.POINTER(c_vp), c_i64, c_vp]),
+    "gcg_spmm_set_tuning": (None, [c_int, c_int]),
 }
 
 _lib = None

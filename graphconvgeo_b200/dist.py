@@ -155,6 +155,65 @@ class DistCSRMatrix:
         return ops.spmm(self.off, full, out=out, accumulate=True, **epi)
 
 
+class _RawCudaArray:
+    def __init__(self, ptr, numel):
+        self.__cuda_array_interface__ = {"shape": (int(numel),), "typestr": "<f4", "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+class PeerBuffers:
+    """IPC-shared staging buffers for the peer-memory transposes (gcg_push_cols_f32 / gcg_push_rows_f32):
+    every rank owns a `recv` buffer ([n_pad, Fp] column slice of all nodes) and a `back` buffer
+    ([P][rows][Fp] row groups coming home) that the PEERS write with plain stores over NVLink."""
+
+    def __init__(self, part: RowPartition, fp_max, rows_max):
+        import ctypes as C
+        from . import _lib
+        L = _lib.lib()
+        self.part = part
+        P = part.world
+        self.recv_floats = int(part.n_pad * fp_max)
+        self.back_floats = int(P * rows_max * fp_max)
+        self._own, handles = [], []
+        for nfl in (self.recv_floats, self.back_floats):
+            ptr = C.c_void_p()
+            h = C.create_string_buffer(64)
+            _lib.check(L.gcg_peer_alloc(nfl * 4, C.byref(ptr), h), "gcg_peer_alloc")
+            self._own.append(ptr.value)
+            handles.append(h.raw)
+        allh = [None] * P
+        dist.all_gather_object(allh, handles, group=part.group)
+        self.recv_ptrs, self.back_ptrs, self._opened = [], [], []
+        for q in range(P):
+            if q == part.rank:
+                self.recv_ptrs.append(self._own[0])
+                self.back_ptrs.append(self._own[1])
+                continue
+            got = []
+            for h in allh[q]:
+                ptr = C.c_void_p()
+                _lib.check(L.gcg_peer_open(C.create_string_buffer(h, 64), C.byref(ptr)), "gcg_peer_open")
+                got.append(ptr.value)
+                self._opened.append(ptr.value)
+            self.recv_ptrs.append(got[0])
+            self.back_ptrs.append(got[1])
+        dev = part.device
+        self.recv_t = torch.as_tensor(_RawCudaArray(self._own[0], self.recv_floats), device=dev)
+        self.back_t = torch.as_tensor(_RawCudaArray(self._own[1], self.back_floats), device=dev)
+        self._flag = torch.zeros(1, dtype=torch.float32, device=dev)
+        self._C = C
+        self._L = L
+
+    def barrier(self):
+        """cross-rank ordering point in stream order (tiny NCCL all-reduce; no host synchronisation)"""
+        dist.all_reduce(self._flag, group=self.part.group)
+
+    def ptr_array(self, ptrs, byte_offsets=None):
+        C = self._C
+        vals = [p + (0 if byte_offsets is None else byte_offsets[i]) for i, p in enumerate(ptrs)]
+        return (C.c_void_p * len(vals))(*vals)
+
+
 class FeatureSplitCSRMatrix:
     """Alternative multi-GPU scheme for A_hat.Z (SURVEY 7.2 "feature-partitioned SpMM"): every rank keeps
     the WHOLE sparse matrix (A_hat is only 8*nnz bytes) and propagates a COLUMN slice Z[:, cols_p] of the
@@ -215,6 +274,11 @@ class FeatureSplitCSRMatrix:
         my_rows = self.row_counts[r]
         if out is None:
             out = ops.alloc_mat(my_rows, F, B.device)
+        peer = getattr(part, "peer", None)
+        rows_total = int(sum(self.row_counts))
+        if peer is not None and part.n_pad * Fp <= peer.recv_floats and P * my_rows * Fp <= peer.back_floats \
+                and all(P * c * Fp <= peer.back_floats for c in self.row_counts):
+            return self._dist_spmm_peer(peer, B, out, bias, act, gate, carry, conv_out, Fp, rows_total, my_rows)
         # 1. row layout -> column slices (zero padded), one all-to-all
         send = self._buf("send", (P, n_loc, Fp))
         ops.pack_cols(B, P, Fp, send)
@@ -227,7 +291,6 @@ class FeatureSplitCSRMatrix:
             bpad = self._buf("bias", (P * Fp,))
             bpad[:F].copy_(bias)
             bs = bpad[r * Fp:(r + 1) * Fp]
-        rows_total = int(sum(self.row_counts))
         outslice = self._buf("outslice", (max(rows_total, 1), Fp))
         if rows_total > 0:
             ops.spmm(self.full, recv, out=outslice[:rows_total], bias=bs, act=act)
@@ -241,6 +304,46 @@ class FeatureSplitCSRMatrix:
         ops.unpack_cols(back[:P * my_rows], P, Fp, dst)
         if gate is not None:
             ops.highway_mix(dst, gate, carry, out=out)       # out = g*Hc + (1-g)*H ; Hc kept in conv_out
+        return out
+
+    def _dist_spmm_peer(self, peer, B, out, bias, act, gate, carry, conv_out, Fp, rows_total, my_rows):
+        """Same propagation with the two transposes done by peer-memory stores (no NCCL all-to-all)."""
+        import ctypes as C
+        from . import _lib
+        L = _lib.lib()
+        part = self.part
+        P, r, n_loc = part.world, part.rank, part.n_loc
+        F = B.shape[1]
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        bp, ldb = ops._mat(B, "B")
+        # 1. every rank writes slice q of its rows into rank q's recv buffer (rows [r*n_loc, (r+1)*n_loc))
+        _lib.check(L.gcg_push_cols_f32(bp, ldb, n_loc, F, P, Fp, peer.ptr_array(peer.recv_ptrs), r * n_loc, stream),
+                   "gcg_push_cols_f32")
+        part.bytes_gathered += (P - 1) * n_loc * Fp * 4
+        peer.barrier()
+        recv = peer.recv_t[:part.n_pad * Fp].view(part.n_pad, Fp)
+        bs = None
+        if bias is not None:
+            bpad = self._buf("bias", (P * Fp,))
+            bpad[:F].copy_(bias)
+            bs = bpad[r * Fp:(r + 1) * Fp]
+        outslice = self._buf("outslice", (max(rows_total, 1), Fp))
+        if rows_total > 0:
+            ops.spmm(self.full, recv, out=outslice[:rows_total], bias=bs, act=act)
+        # 2. row group of owner q goes to slot r of rank q's back buffer ([P][row_counts[q]][Fp])
+        off = np.zeros(P + 1, np.int64)
+        np.cumsum(self.row_counts, out=off[1:])
+        offs = (C.c_int64 * (P + 1))(*[int(x) for x in off])
+        dst_ptrs = peer.ptr_array(peer.back_ptrs, [r * self.row_counts[q] * Fp * 4 for q in range(P)])
+        _lib.check(L.gcg_push_rows_f32(C.c_void_p(outslice.data_ptr()), offs, P, Fp, dst_ptrs, 0, stream),
+                   "gcg_push_rows_f32")
+        peer.barrier()
+        if my_rows == 0:
+            return out
+        dst = out if gate is None or conv_out is None else conv_out
+        ops.unpack_cols(peer.back_t[:P * my_rows * Fp], P, Fp, dst)
+        if gate is not None:
+            ops.highway_mix(dst, gate, carry, out=out)
         return out
 
 
@@ -280,11 +383,14 @@ class DistMLPCONV(MLPCONV):
     single-process fit() is); each keeps its row block.  Results (loss, acc, predictions gathered
     over ranks, parameters) equal the single-GPU ones up to summation order of the all-reduces."""
 
-    def __init__(self, *args, group=None, partition="feature", **kwargs):
+    def __init__(self, *args, group=None, partition="auto", peer_memory=True, **kwargs):
         kwargs["cuda_graph"] = False          # NCCL work is enqueued eagerly
         super().__init__(*args, **kwargs)
-        assert partition in ("row", "feature")
+        assert partition in ("row", "feature", "auto")
+        if partition == "auto":               # measured on B200: the all-gather wins at 2 ranks, the transposes from 4 up
+            partition = "feature" if dist.get_world_size(group) >= 4 else "row"
         self.partition = partition            # how A_hat.Z is distributed (see the two matrix classes)
+        self.peer_memory = peer_memory        # feature mode: transposes by P2P stores instead of NCCL all-to-all
         self.group = group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
@@ -320,6 +426,20 @@ class DistMLPCONV(MLPCONV):
         part = RowPartition(n, self.world, self.rank, self.device, self.group)
         self.part = part
         Hd = (FeatureSplitCSRMatrix if self.partition == "feature" else DistCSRMatrix).from_global(Hg, part)
+        part.peer = None
+        if self.partition == "feature" and self.peer_memory and self.world > 1:
+            f_max = max(int(self.hidden_layer_size), out_size)
+            fp_max = (-(-f_max // self.world) + 3) // 4 * 4
+            try:
+                part.peer = PeerBuffers(part, fp_max, rows_max=part.n_loc + part.n_loc // 8 + 64)
+            except Exception as e:          # no P2P / IPC on this box: NCCL all-to-all path
+                import logging
+                logging.getLogger("graphconvgeo_b200").warning("peer-memory transposes unavailable (%s); using NCCL", e)
+                part.peer = None
+            ok = torch.tensor([1.0 if part.peer is not None else 0.0], device=self.device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+            if ok.item() < 1.0:
+                part.peer = None
         # local rows of X (padded with empty rows)
         ip, ix, d = Xg._host_arrays()
         p = np.zeros(part.n_loc + 1, np.int32)

@@ -203,6 +203,26 @@ int gcg_pack_cols_f32(const float* src, int64_t ld, int64_t n_rows, int64_t F, i
 int gcg_unpack_cols_f32(const float* src, int64_t n_rows, int64_t F, int32_t P, int64_t Fp, float* dst,
                         int64_t ld, void* stream);
 
+/* Peer-memory (NVLink P2P) variant of the two transposes: each rank WRITES its slices straight into the
+ * peers' buffers (IPC-mapped device pointers, plain stores over NVLink), one kernel per direction, no
+ * collective launch; the caller orders visibility with a cross-rank barrier in stream order.
+ *  gcg_peer_alloc/open/close/free: cudaMalloc + 64-byte cudaIpcMemHandle exchange helpers.
+ *  push_cols: dst_q[(dst_row0 + i), :Fp] = src[i, q*Fp:(q+1)*Fp]   for every peer q (zero padded)
+ *  push_rows: dst_q[slot_offset + i*Fp ...] = src[row_off[q] + i, :Fp], i < row_off[q+1]-row_off[q]
+ * h_peer_dst: host array of P device pointers (peer q's buffer as mapped in THIS process). */
+int gcg_peer_alloc(int64_t bytes, void** d_ptr, void* handle64);
+int gcg_peer_free(void* d_ptr);
+int gcg_peer_open(const void* handle64, void** d_ptr);
+int gcg_peer_close(void* d_ptr);
+int gcg_push_cols_f32(const float* src, int64_t ld, int64_t n_rows, int64_t F, int32_t P, int64_t Fp,
+                      void* const* h_peer_dst, int64_t dst_row0, void* stream);
+int gcg_push_rows_f32(const float* src, const int64_t* h_row_off, int32_t P, int64_t Fp,
+                      void* const* h_peer_dst, int64_t slot_offset_floats, void* stream);
+
+/* SpMM tuning knob for experiments (scripts/spmm_sweep.py): u = gathered rows in flight per lane group,
+ * minb = __launch_bounds__ min blocks (0 = compiler's choice); (0, 0) restores the defaults. */
+void gcg_spmm_set_tuning(int u, int minb);
+
 /* ---------------------------------------------------------------- optimiser */
 
 /* One fused multi-tensor step of lasagne.updates.adam (mlpconv.py:263) with the

@@ -23,8 +23,9 @@ def gpu_main():
     import datetime
     dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=120))
     w = synth.make_workload("tiny")
-    for n_layers, highway, reorder, partition in ((2, False, None, "row"), (3, True, "labels", "row"),
-                                                   (2, False, "labels", "feature"), (3, True, None, "feature")):
+    for n_layers, highway, reorder, partition, peer in ((2, False, None, "row", False), (3, True, "labels", "row", False),
+                                                         (2, False, "labels", "feature", False), (3, True, None, "feature", False),
+                                                         (3, True, "labels", "feature", True), (2, False, None, "feature", True)):
         rng = np.random.RandomState(5)
         params = go.init_params(rng, w.X.shape[1], w.hidden, w.n_classes, n_layers, highway)
         idx = rng.choice(w.train_indices, size=len(w.train_indices)).astype(np.int32)      # duplicates
@@ -34,7 +35,7 @@ def gpu_main():
         hist = go.train_epochs(net, ref_params, idx, y, 3)
         m = DistMLPCONV(n_epochs=1, regul_coefs=[1e-4, 2e-4], hidden_layer_size=w.hidden, n_layers=n_layers,
                         highway=highway, init_parameters=[p.copy() for p in params], device=dev, reorder=reorder,
-                        partition=partition)
+                        partition=partition, peer_memory=peer)
         m.prepare(w.X, idx, w.dev_indices, w.test_indices, w.Y, w.A_hat)
         assert m.part.world == world
         for step in range(3):
@@ -61,7 +62,7 @@ def gpu_main():
         _, ref_acc = net.loss_acc(ref_params, w.test_indices, w.Y[w.test_indices].astype(np.int32))
         assert abs(acc - ref_acc) <= 2.0 / len(w.test_indices)
         if rank == 0:
-            print("dist case", n_layers, highway, reorder, partition, "OK", flush=True)
+            print("dist case", n_layers, highway, reorder, partition, "peer" if (peer and m.part.peer is not None) else "nccl", "OK", flush=True)
     dist.barrier()
     dist.destroy_process_group()
     if rank == 0:
