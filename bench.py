@@ -239,6 +239,16 @@ def run_gpu(args):
     m._graph = m_graph
 
     breakdown = op_breakdown(m, dev) if args.breakdown else None       # collective-safe: every rank runs it
+    if world > 1 and os.environ.get("GCG_DIST_PROFILE") == "1":
+        from graphconvgeo_b200.dist import phase_profile
+        phase_profile.acc.clear()
+        phase_profile.pending = []
+        m._train_step_enqueue()
+        rep = phase_profile.report()
+        if rank == 0:
+            log("---- phases of the feature-sliced propagation over one epoch (rank 0) ----")
+            for k, v in rep.items():
+                log("  %-10s x%-3d %8.3f ms" % (k, v["calls"], v["ms"]))
 
     # ---------------- e2e: host inputs re-uploaded every epoch, loss/acc read back
     e2e = None

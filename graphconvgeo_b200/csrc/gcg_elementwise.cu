@@ -164,38 +164,45 @@ __global__ void __launch_bounds__(256) highway_fwd_kernel(const float* __restric
 
 // ----------------------------------------------------- column-slice pack / unpack
 // row layout [n, F] <-> P column slices [P][n][Fp] (zero padded), the two transposes around the
-// feature-sliced multi-GPU propagation.  One float4 of the sliced side per thread.
+// feature-sliced multi-GPU propagation.
+// one warp per row, lanes over the P*Fp/4 float4 of the sliced side: no 64-bit divisions in the loop
 __global__ void __launch_bounds__(256) pack_cols_kernel(const float* __restrict__ src, int64_t ld, int64_t n,
                                                         int64_t F, int P, int64_t Fp, float* __restrict__ dst) {
-  const int64_t fp4 = Fp >> 2, total = (int64_t)P * n * fp4;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t q = i / (n * fp4), rem = i - q * n * fp4, r = rem / fp4, c4 = rem - r * fp4;
-    const int64_t col = q * Fp + c4 * 4;
-    const float* s = src + r * ld + col;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (col + 3 < F) v = *reinterpret_cast<const float4*>(s);
-    else {
-      if (col < F) v.x = s[0];
-      if (col + 1 < F) v.y = s[1];
-      if (col + 2 < F) v.z = s[2];
+  const int lane = threadIdx.x & 31;
+  const int fp4 = (int)(Fp >> 2), row_f4 = P * fp4;
+  for (int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); r < n; r += (int64_t)gridDim.x * 8) {
+    const float* srow = src + r * ld;
+    for (int j = lane; j < row_f4; j += 32) {
+      const int q = j / fp4, c4 = j - q * fp4;
+      const int64_t col = (int64_t)q * Fp + c4 * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (col + 3 < F) v = *reinterpret_cast<const float4*>(srow + col);
+      else {
+        if (col < F) v.x = srow[col];
+        if (col + 1 < F) v.y = srow[col + 1];
+        if (col + 2 < F) v.z = srow[col + 2];
+      }
+      reinterpret_cast<float4*>(dst + ((int64_t)q * n + r) * Fp)[c4] = v;
     }
-    reinterpret_cast<float4*>(dst)[i] = v;
   }
 }
 __global__ void __launch_bounds__(256) unpack_cols_kernel(const float* __restrict__ src, int64_t n, int64_t F, int P,
                                                           int64_t Fp, float* __restrict__ dst, int64_t ld) {
-  const int64_t fp4 = Fp >> 2, total = (int64_t)P * n * fp4;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t q = i / (n * fp4), rem = i - q * n * fp4, r = rem / fp4, c4 = rem - r * fp4;
-    const int64_t col = q * Fp + c4 * 4;
-    if (col >= F) continue;
-    const float4 v = reinterpret_cast<const float4*>(src)[i];
-    float* d = dst + r * ld + col;
-    if (col + 3 < F) *reinterpret_cast<float4*>(d) = v;
-    else {
-      d[0] = v.x;
-      if (col + 1 < F) d[1] = v.y;
-      if (col + 2 < F) d[2] = v.z;
+  const int lane = threadIdx.x & 31;
+  const int fp4 = (int)(Fp >> 2), row_f4 = P * fp4;
+  for (int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); r < n; r += (int64_t)gridDim.x * 8) {
+    float* drow = dst + r * ld;
+    for (int j = lane; j < row_f4; j += 32) {
+      const int q = j / fp4, c4 = j - q * fp4;
+      const int64_t col = (int64_t)q * Fp + c4 * 4;
+      if (col >= F) continue;
+      const float4 v = reinterpret_cast<const float4*>(src + ((int64_t)q * n + r) * Fp)[c4];
+      if (col + 3 < F) *reinterpret_cast<float4*>(drow + col) = v;
+      else {
+        drow[col] = v.x;
+        if (col + 1 < F) drow[col + 1] = v.y;
+        if (col + 2 < F) drow[col + 2] = v.z;
+      }
     }
   }
 }
@@ -618,7 +625,7 @@ extern "C" int gcg_pack_cols_f32(const float* src, int64_t ld, int64_t n_rows, i
   GCG_CHECK_SHAPE(Fp % 4 == 0 && ld % 4 == 0 && ld >= F && (int64_t)P * Fp >= F && aligned16(src) && aligned16(dst),
                   "gcg_pack_cols_f32: needs 16-byte aligned operands, ld %% 4 == 0, Fp %% 4 == 0");
   if (n_rows == 0) return GCG_OK;
-  pack_cols_kernel<<<grid_for((int64_t)P * n_rows * (Fp / 4), 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  pack_cols_kernel<<<grid_for(n_rows * 32, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       src, ld, n_rows, F, P, Fp, dst);
   GCG_LAUNCH_CHECK();
   return GCG_OK;
@@ -630,7 +637,7 @@ extern "C" int gcg_unpack_cols_f32(const float* src, int64_t n_rows, int64_t F, 
   GCG_CHECK_SHAPE(Fp % 4 == 0 && ld % 4 == 0 && ld >= F && (int64_t)P * Fp >= F && aligned16(src) && aligned16(dst),
                   "gcg_unpack_cols_f32: needs 16-byte aligned operands, ld %% 4 == 0, Fp %% 4 == 0");
   if (n_rows == 0) return GCG_OK;
-  unpack_cols_kernel<<<grid_for((int64_t)P * n_rows * (Fp / 4), 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  unpack_cols_kernel<<<grid_for(n_rows * 32, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       src, n_rows, F, P, Fp, dst, ld);
   GCG_LAUNCH_CHECK();
   return GCG_OK;

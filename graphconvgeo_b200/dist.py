@@ -155,6 +155,43 @@ class DistCSRMatrix:
         return ops.spmm(self.off, full, out=out, accumulate=True, **epi)
 
 
+class _PhaseProfile:
+    """GCG_DIST_PROFILE=1: CUDA-event timing of the phases of the feature-sliced propagation (rank 0 prints)."""
+
+    def __init__(self):
+        import os
+        self.on = os.environ.get("GCG_DIST_PROFILE") == "1"
+        self.acc = {}
+        self.pending = []
+
+    def mark(self, name):
+        if not self.on:
+            return
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        self.pending.append((name, e))
+
+    def flush(self):
+        if not self.on or len(self.pending) < 2:
+            self.pending = []
+            return
+        torch.cuda.synchronize()
+        for (n0, e0), (n1, e1) in zip(self.pending[:-1], self.pending[1:]):
+            if n1 == "start":
+                continue
+            a = self.acc.setdefault(n1, [0, 0.0])
+            a[0] += 1
+            a[1] += e0.elapsed_time(e1)
+        self.pending = []
+
+    def report(self):
+        self.flush()
+        return {k: {"calls": c, "ms": t} for k, (c, t) in self.acc.items()}
+
+
+phase_profile = _PhaseProfile()
+
+
 class _RawCudaArray:
     def __init__(self, ptr, numel):
         self.__cuda_array_interface__ = {"shape": (int(numel),), "typestr": "<f4", "data": (int(ptr), False),
@@ -316,11 +353,15 @@ class FeatureSplitCSRMatrix:
         F = B.shape[1]
         stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
         bp, ldb = ops._mat(B, "B")
+        pp = phase_profile
+        pp.mark("start")
         # 1. every rank writes slice q of its rows into rank q's recv buffer (rows [r*n_loc, (r+1)*n_loc))
         _lib.check(L.gcg_push_cols_f32(bp, ldb, n_loc, F, P, Fp, peer.ptr_array(peer.recv_ptrs), r * n_loc, stream),
                    "gcg_push_cols_f32")
         part.bytes_gathered += (P - 1) * n_loc * Fp * 4
+        pp.mark("push_cols")
         peer.barrier()
+        pp.mark("barrier1")
         recv = peer.recv_t[:part.n_pad * Fp].view(part.n_pad, Fp)
         bs = None
         if bias is not None:
@@ -330,6 +371,7 @@ class FeatureSplitCSRMatrix:
         outslice = self._buf("outslice", (max(rows_total, 1), Fp))
         if rows_total > 0:
             ops.spmm(self.full, recv, out=outslice[:rows_total], bias=bs, act=act)
+        pp.mark("spmm")
         # 2. row group of owner q goes to slot r of rank q's back buffer ([P][row_counts[q]][Fp])
         off = np.zeros(P + 1, np.int64)
         np.cumsum(self.row_counts, out=off[1:])
@@ -337,13 +379,16 @@ class FeatureSplitCSRMatrix:
         dst_ptrs = peer.ptr_array(peer.back_ptrs, [r * self.row_counts[q] * Fp * 4 for q in range(P)])
         _lib.check(L.gcg_push_rows_f32(C.c_void_p(outslice.data_ptr()), offs, P, Fp, dst_ptrs, 0, stream),
                    "gcg_push_rows_f32")
+        pp.mark("push_rows")
         peer.barrier()
+        pp.mark("barrier2")
         if my_rows == 0:
             return out
         dst = out if gate is None or conv_out is None else conv_out
         ops.unpack_cols(peer.back_t[:P * my_rows * Fp], P, Fp, dst)
         if gate is not None:
             ops.highway_mix(dst, gate, carry, out=out)
+        pp.mark("unpack")
         return out
 
 

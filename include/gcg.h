@@ -204,8 +204,8 @@ int gcg_unpack_cols_f32(const float* src, int64_t n_rows, int64_t F, int32_t P, 
                         int64_t ld, void* stream);
 
 /* Peer-memory (NVLink P2P) variant of the two transposes: each rank WRITES its slices straight into the
- * peers' buffers (IPC-mapped device pointers, plain stores over NVLink), one kernel per direction, no
- * collective launch; the caller orders visibility with a cross-rank barrier in stream order.
+ * peers' buffers (IPC-mapped device pointers, 128-bit stores over NVLink, one kernel per direction),
+ * no staging copy and no collective; the caller orders visibility with a cross-rank barrier.
  *  gcg_peer_alloc/open/close/free: cudaMalloc + 64-byte cudaIpcMemHandle exchange helpers.
  *  push_cols: dst_q[(dst_row0 + i), :Fp] = src[i, q*Fp:(q+1)*Fp]   for every peer q (zero padded)
  *  push_rows: dst_q[slot_offset + i*Fp ...] = src[row_off[q] + i, :Fp], i < row_off[q+1]-row_off[q]
