@@ -251,9 +251,14 @@ def run_gpu(args):
                 log("  %-10s x%-3d %8.3f ms" % (k, v["calls"], v["ms"]))
 
     # ---------------- e2e: host inputs re-uploaded every epoch, loss/acc read back
-    e2e = None
-    if world == 1:
-        e2e = measure_e2e(m, args, dev, flush)
+    e2e = measure_e2e(m, args, dev, flush)        # every rank re-uploads its own row block
+    if world > 1:
+        t = torch.tensor([e2e["value"], float(e2e["h2d_bytes_per_step"])], device=dev, dtype=torch.float64)
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        e2e["value"] = float(tmax[0].item())                      # max over ranks
+        e2e["h2d_bytes_per_step"] = int(t[1].item())              # summed over ranks
 
     # ---------------- roofline of the headline kernel: A_hat . H  (F = hidden)
     roof = spmm_roofline(m, wl, dev)          # collective in row-partitioned mode: every rank calls it
