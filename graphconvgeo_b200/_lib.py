@@ -40,6 +40,10 @@ PROTOTYPES = {
                                  c_vp, c_i64, c_vp, c_i64, c_i32, c_vp, c_i64, c_vp]),
     "gcg_gemm_f32": (c_int, [c_int, c_int, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_f32,
                              c_vp, c_int, c_vp, c_i64, c_int, c_int, c_i32, c_vp, c_i64, c_vp]),
+    "gcg_gemm_presplit_f32": (c_int, [c_int, c_int, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_f32,
+                                      c_vp, c_int, c_vp, c_i64, c_int, c_int, c_i32, c_vp, c_i64, c_vp,
+                                      c_vp, c_vp, c_vp, c_vp]),
+    "gcg_tf32_split_f32": (c_int, [c_vp, c_i64, c_i64, c_vp, c_vp, c_vp]),
     "gcg_gemm_workspace_bytes": (c_i64, [c_int, c_int, c_i64, c_i64, c_i64, c_int, c_i32]),
     "gcg_gemm_tc_available": (c_int, []),
     "gcg_colsum_f32": (c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_i64, c_vp]),

@@ -191,11 +191,38 @@ extern "C" int64_t gcg_gemm_workspace_bytes(int transA, int transB, int64_t M, i
   return std::max(fma_bytes, gemm_tc_workspace_bytes(transA, transB, M, N, K, mode, split_k));
 }
 
+static int gemm_impl(int transA, int transB, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda,
+                     const float* B, int64_t ldb, float* C, int64_t ldc, float beta, const float* bias, int act,
+                     const float* mask, int64_t ld_mask, int mask_act, int mode, int32_t split_k, void* workspace,
+                     int64_t workspace_bytes, void* stream, const float* A_hi, const float* A_lo,
+                     const float* B_hi, const float* B_lo);
+
 extern "C" int gcg_gemm_f32(int transA, int transB, int64_t M, int64_t N, int64_t K,
                             const float* A, int64_t lda, const float* B, int64_t ldb, float* C,
                             int64_t ldc, float beta, const float* bias, int act, const float* mask,
                             int64_t ld_mask, int mask_act, int mode, int32_t split_k,
                             void* workspace, int64_t workspace_bytes, void* stream) {
+  return gemm_impl(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, beta, bias, act, mask, ld_mask, mask_act, mode,
+                   split_k, workspace, workspace_bytes, stream, nullptr, nullptr, nullptr, nullptr);
+}
+
+extern "C" int gcg_gemm_presplit_f32(int transA, int transB, int64_t M, int64_t N, int64_t K,
+                                     const float* A, int64_t lda, const float* B, int64_t ldb, float* C,
+                                     int64_t ldc, float beta, const float* bias, int act, const float* mask,
+                                     int64_t ld_mask, int mask_act, int mode, int32_t split_k,
+                                     void* workspace, int64_t workspace_bytes, void* stream,
+                                     const float* A_hi, const float* A_lo, const float* B_hi, const float* B_lo) {
+  GCG_CHECK_ARG((A_hi == nullptr) == (A_lo == nullptr) && (B_hi == nullptr) == (B_lo == nullptr),
+                "gcg_gemm_presplit_f32: hi and lo go together");
+  return gemm_impl(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, beta, bias, act, mask, ld_mask, mask_act, mode,
+                   split_k, workspace, workspace_bytes, stream, A_hi, A_lo, B_hi, B_lo);
+}
+
+static int gemm_impl(int transA, int transB, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda,
+                     const float* B, int64_t ldb, float* C, int64_t ldc, float beta, const float* bias, int act,
+                     const float* mask, int64_t ld_mask, int mask_act, int mode, int32_t split_k, void* workspace,
+                     int64_t workspace_bytes, void* stream, const float* A_hi, const float* A_lo,
+                     const float* B_hi, const float* B_lo) {
   GCG_CHECK_ARG(A && B && C, "gcg_gemm_f32: NULL operand");
   GCG_CHECK_SHAPE(M >= 0 && N >= 0 && K >= 0, "gcg_gemm_f32: negative dimension");
   GCG_CHECK_SHAPE(lda >= (transA ? M : K) && ldb >= (transB ? K : N) && ldc >= N,
@@ -216,6 +243,7 @@ extern "C" int gcg_gemm_f32(int transA, int transB, int64_t M, int64_t N, int64_
   g.vecA = aligned16(A) && lda % 4 == 0;
   g.vecB = aligned16(B) && ldb % 4 == 0;
   g.vecC = aligned16(C) && ldc % 4 == 0;
+  g.A_hi = A_hi; g.A_lo = A_lo; g.B_hi = B_hi; g.B_lo = B_lo;
   const int32_t split_req = split_k;
   if (mode != GCG_GEMM_FMA && K > 0) {
     g.split_k = split_req > 0 ? split_req : gemm_tc_auto_split(M, N, K);

@@ -16,6 +16,8 @@ struct GemmArgs {
   int split_k; int64_t k_per_split;
   float* part;  // split-K partials [split][M][N]
   int vecA, vecB, vecC;
+  // optional pre-split tf32 operands (same leading dimensions as A / B); NULL = split inside the call
+  const float *A_hi, *A_lo, *B_hi, *B_lo;
 };
 
 
@@ -36,5 +38,6 @@ int gemm_tc_launch(const GemmArgs& g, int transA, int transB, int mode, void* wo
 int64_t gemm_tc_workspace_bytes(int transA, int transB, int64_t M, int64_t N, int64_t K, int mode,
                                 int split_k);
 int gemm_tc_auto_split(int64_t M, int64_t N, int64_t K);
+int tf32_split_launch(const float* x, int64_t n_floats, float* hi, float* lo, cudaStream_t st);
 
 }  // namespace gcg

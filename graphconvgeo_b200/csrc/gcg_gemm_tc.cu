@@ -403,6 +403,14 @@ __global__ void __launch_bounds__(256) split_tf32_kernel(const float* __restrict
   }
 }
 
+int tf32_split_launch(const float* x, int64_t n_floats, float* hi, float* lo, cudaStream_t st) {
+  const int64_t n4 = n_floats / 4;
+  if (n4 == 0) return GCG_OK;
+  split_tf32_kernel<<<(unsigned)std::min<int64_t>(ceil_div(n4, 256), (int64_t)kNumSMs * 16), 256, 0, st>>>(x, hi, lo, n4);
+  GCG_LAUNCH_CHECK();
+  return GCG_OK;
+}
+
 // ------------------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -494,10 +502,13 @@ int gemm_tc_launch(const GemmArgs& g0, int transA, int transB, int mode, void* w
   };
   const float *Ah = g.A, *Bh = g.B;
   float *Al = nullptr, *Bl = nullptr, *Ahx = nullptr, *Bhx = nullptr;
-  if (x3) {
+  const bool split_a = x3 && !(g.A_hi && g.A_lo), split_b = x3 && !(g.B_hi && g.B_lo);
+  if (split_a) {
     Al = carve(a_rows * g.lda * 4);
-    Bl = carve(b_rows * g.ldb * 4);
     Ahx = carve(a_rows * g.lda * 4);       // the round-to-nearest split needs its own hi copy
+  }
+  if (split_b) {
+    Bl = carve(b_rows * g.ldb * 4);
     Bhx = carve(b_rows * g.ldb * 4);
   }
   int split = g.split_k;
@@ -510,13 +521,22 @@ int gemm_tc_launch(const GemmArgs& g0, int transA, int transB, int mode, void* w
   if (off > workspace_bytes || (off > 0 && (!workspace || !aligned16(workspace)))) return GCG_ERR_UNSUPPORTED;
 
   if (x3) {
-    const int64_t na4 = a_rows * g.lda / 4, nb4 = b_rows * g.ldb / 4;
-    split_tf32_kernel<<<(unsigned)std::min<int64_t>(ceil_div(na4, 256), (int64_t)kNumSMs * 16), 256, 0, st>>>(g.A, Ahx, Al, na4);
-    GCG_LAUNCH_CHECK();
-    split_tf32_kernel<<<(unsigned)std::min<int64_t>(ceil_div(nb4, 256), (int64_t)kNumSMs * 16), 256, 0, st>>>(g.B, Bhx, Bl, nb4);
-    GCG_LAUNCH_CHECK();
-    Ah = Ahx;
-    Bh = Bhx;
+    if (split_a) {
+      const int rc = tf32_split_launch(g.A, a_rows * g.lda, Ahx, Al, st);
+      if (rc != GCG_OK) return rc;
+      Ah = Ahx;
+    } else {
+      Ah = g.A_hi;
+      Al = const_cast<float*>(g.A_lo);
+    }
+    if (split_b) {
+      const int rc = tf32_split_launch(g.B, b_rows * g.ldb, Bhx, Bl, st);
+      if (rc != GCG_OK) return rc;
+      Bh = Bhx;
+    } else {
+      Bh = g.B_hi;
+      Bl = const_cast<float*>(g.B_lo);
+    }
   }
   CUtensorMap mAh, mAl, mBh, mBl;
   const int a_box = transA ? 32 : TM, b_box = transB ? TN : 32;   // MN-major operands load {32 MN, 32 K} boxes
@@ -562,6 +582,13 @@ int gemm_tc_launch(const GemmArgs& g0, int transA, int transB, int mode, void* w
 }
 
 }  // namespace gcg
+
+extern "C" int gcg_tf32_split_f32(const float* x, int64_t ld, int64_t n_rows, float* hi, float* lo, void* stream) {
+  GCG_CHECK_ARG(x && hi && lo && n_rows >= 0, "gcg_tf32_split_f32: NULL argument");
+  GCG_CHECK_SHAPE(ld % 4 == 0 && gcg::aligned16(x) && gcg::aligned16(hi) && gcg::aligned16(lo),
+                  "gcg_tf32_split_f32: needs 16-byte aligned operands and ld %% 4 == 0");
+  return gcg::tf32_split_launch(x, n_rows * ld, hi, lo, reinterpret_cast<cudaStream_t>(stream));
+}
 
 extern "C" int gcg_gemm_tc_available(void) {
   int dev = 0, major = 0;

@@ -194,6 +194,17 @@ class DenseLayer(Layer):
         return ops.gemm(input, self.W, bias=self.b, act=self.nonlinearity,
                         out=self._mat("out", input.shape[0], self.num_units))
 
+    def _split(self, key, t, other_dim):
+        """tf32 hi/lo split of an activation that several tcgen05 GEMMs of this step read (None when the
+        contraction is small enough for the FFMA engine)."""
+        if not ops.gemm_uses_tensor_cores(t.shape[0], t.shape[1], other_dim):
+            return None
+        if not hasattr(self, "_splits"):
+            self._splits = {}
+        sp = ops.tf32_split(t, like=self._splits.get(key))
+        self._splits[key] = sp
+        return sp
+
     def _grad(self, key, like):
         g = self.grads.get(key)
         if g is None:
@@ -353,8 +364,9 @@ class ConvolutionDenseLayer(_ConvBase):
         n_out = N if ti is None else ti.n
         q = ops.spmm(Hm, input, out=self._mat(("Q", n_out), n_out, self.num_inputs))      # H[idx,:].input
         self._q = q
+        self._s_q = self._split(("q", n_out), q, self.num_units)
         fused_act = "identity" if self.nonlinearity == "softmax" else self.nonlinearity
-        out = ops.gemm(q, self.W, bias=self.b, act=fused_act,
+        out = ops.gemm(q, self.W, bias=self.b, act=fused_act, a_split=self._s_q,
                        out=self._mat(("out", n_out), n_out, self.num_units))               # (.).W + b
         self._out = out
         if self.nonlinearity == "softmax" and not kwargs.get("logits", False):
@@ -372,10 +384,12 @@ class ConvolutionDenseLayer(_ConvBase):
             dPr = ops.act_bwd(grad_output, self._out, self.nonlinearity, out=self._mat("dPr", *grad_output.shape))
         if self.b is not None:
             ops.colsum(dPr, out=self._grad("b", self.b))
-        ops.gemm(self._q, dPr, transA=True, out=self._grad("W", self.W))                   # dW = Q^T.dP
+        s_g = self._split(("dPr", dPr.shape[0]), dPr, self.num_inputs)
+        ops.gemm(self._q, dPr, transA=True, out=self._grad("W", self.W), a_split=self._s_q, b_split=s_g)   # dW = Q^T.dP
         if not need_input_grad:
             return None
-        dQ = ops.gemm(dPr, self.W, transB=True, out=self._mat(("dQ", dPr.shape[0]), dPr.shape[0], self.num_inputs))
+        dQ = ops.gemm(dPr, self.W, transB=True, a_split=s_g,
+                      out=self._mat(("dQ", dPr.shape[0]), dPr.shape[0], self.num_inputs))
         if ti is not None:
             ptr, pos = ti.positions
             S = ops.scatter_rows(dQ, ptr, pos, N, out=self._operand("dP", N, self.num_inputs))
@@ -393,7 +407,8 @@ class ConvolutionDenseLayer(_ConvBase):
         self._ti = ti
         if self.propagate_first:
             return self._forward_propagate_first(input, ti, kwargs)
-        z = ops.gemm(input, self.W, out=self._operand("Z", N, self.num_units))   # :82
+        self._s_in = self._split("in", input, self.num_units)
+        z = ops.gemm(input, self.W, out=self._operand("Z", N, self.num_units), a_split=self._s_in)   # :82
         Hm = self.H if ti is None else ti.Hsub
         n_out = N if ti is None else ti.n
         fused_act = "identity" if self.nonlinearity == "softmax" else self.nonlinearity
@@ -427,11 +442,13 @@ class ConvolutionDenseLayer(_ConvBase):
         if self.b is not None:
             ops.colsum(dP, out=self._grad("b", self.b))
         dZ = ops.spmm(self.H, dP, out=self._operand("Z", N, self.num_units))     # A_hat^T.dP
-        ops.gemm(self._in, dZ, transA=True, out=self._grad("W", self.W))     # dW = H_in^T.dZ
+        s_dz = self._split("dZ", dZ, self.num_inputs)
+        ops.gemm(self._in, dZ, transA=True, out=self._grad("W", self.W),
+                 a_split=self._s_in, b_split=s_dz)                           # dW = H_in^T.dZ
         if not need_input_grad:
             return None
         mk, mact = (None, "identity") if input_mask is None else input_mask
-        return ops.gemm(dZ, self.W, transB=True, mask=mk, mask_act=mact,
+        return ops.gemm(dZ, self.W, transB=True, mask=mk, mask_act=mact, a_split=s_dz,
                         out=self._mat("dIn", N, self.num_inputs))            # dH = dZ.W^T
 
 
@@ -456,8 +473,9 @@ class HighwayConvolutionDenseLayer(ConvolutionDenseLayer):
         assert kwargs.get("target_indices") is None, "a gated layer keeps all rows"
         N, h = input.shape[0], self.num_units
         self._in = input
-        z = ops.gemm(input, self.W, out=self._operand("Z", N, h))
-        g = ops.gemm(input, self.Wg, bias=self.bg, act="sigmoid", out=self._mat("g", N, h))
+        self._s_in = self._split("in", input, h)                  # one hi/lo split feeds four GEMMs (fwd 2, bwd 2)
+        z = ops.gemm(input, self.W, out=self._operand("Z", N, h), a_split=self._s_in)
+        g = ops.gemm(input, self.Wg, bias=self.bg, act="sigmoid", out=self._mat("g", N, h), a_split=self._s_in)
         conv = self._mat("Hc", N, h) if kwargs.get("train", False) else None
         out = ops.spmm(self.H, z, bias=self.b, act=self.nonlinearity, gate=g, carry=input, conv_out=conv,
                        out=self._mat("out", N, h))
@@ -473,11 +491,12 @@ class HighwayConvolutionDenseLayer(ConvolutionDenseLayer):
         ops.colsum(dP, out=self._grad("b", self.b))
         ops.colsum(dG, out=self._grad("bg", self.bg))
         dZ = ops.spmm(self.H, dP, out=self._operand("Z", N, h))
-        ops.gemm(self._in, dZ, transA=True, out=self._grad("W", self.W))
-        ops.gemm(self._in, dG, transA=True, out=self._grad("Wg", self.Wg))
-        ops.gemm(dZ, self.W, transB=True, beta=1.0, out=dIn)
+        s_dz, s_dg = self._split("dZ", dZ, h), self._split("dG", dG, h)
+        ops.gemm(self._in, dZ, transA=True, out=self._grad("W", self.W), a_split=self._s_in, b_split=s_dz)
+        ops.gemm(self._in, dG, transA=True, out=self._grad("Wg", self.Wg), a_split=self._s_in, b_split=s_dg)
+        ops.gemm(dZ, self.W, transB=True, beta=1.0, out=dIn, a_split=s_dz)
         mk, mact = (None, "identity") if input_mask is None else input_mask
-        ops.gemm(dG, self.Wg, transB=True, beta=1.0, mask=mk, mask_act=mact, out=dIn)
+        ops.gemm(dG, self.Wg, transB=True, beta=1.0, mask=mk, mask_act=mact, out=dIn, a_split=s_dg)
         return dIn
 
 

@@ -156,8 +156,38 @@ def gemm_mode_for(M, N, K):
     return _lib.GEMM_MODE["fma"]
 
 
+class SplitOperand:
+    """tf32 hi/lo copies of a matrix (gcg_tf32_split_f32), reusable by every GEMM that reads it."""
+
+    def __init__(self, src, hi=None, lo=None):
+        sp, ld = _mat(src, "src")
+        n, c = src.shape
+        self.hi = alloc_mat(n, c, src.device) if hi is None else hi
+        self.lo = alloc_mat(n, c, src.device) if lo is None else lo
+        hp, ldh = _mat(self.hi, "hi")
+        lp, ldl = _mat(self.lo, "lo")
+        self.valid = (ldh == ld and ldl == ld and ld % 4 == 0)
+        self.ptr, self.ld, self.shape = src.data_ptr(), ld, tuple(src.shape)
+        if self.valid:
+            _lib.check(_lib.lib().gcg_tf32_split_f32(sp, ld, n, hp, lp, _stream()), "gcg_tf32_split_f32")
+
+    def matches(self, t, ld):
+        return self.valid and t.data_ptr() == self.ptr and tuple(t.shape) == self.shape and ld == self.ld
+
+
+def tf32_split(src, like=None):
+    """Split ``src`` once for several tcgen05 GEMMs; ``like`` reuses a previous SplitOperand's buffers."""
+    if like is not None and like.hi.shape == src.shape:
+        return SplitOperand(src, like.hi, like.lo)
+    return SplitOperand(src)
+
+
+def gemm_uses_tensor_cores(M, N, K):
+    return gemm_mode_for(M, N, K) == _lib.GEMM_MODE["tf32x3"]
+
+
 def gemm(A, B, out=None, transA=False, transB=False, beta=0.0, bias=None, act="identity", mask=None,
-         mask_act="identity", mode=None, split_k=0):
+         mask_act="identity", mode=None, split_k=0, a_split=None, b_split=None):
     """out = act(op(A) @ op(B) + beta*out + bias) [* act'(mask)] -- gcg_gemm_f32 (T.dot, lasagne_layers.py:82)."""
     L = _lib.lib()
     ap, lda = _mat(A, "A")
@@ -182,6 +212,17 @@ def gemm(A, B, out=None, transA=False, transB=False, beta=0.0, bias=None, act="i
         mode = _lib.GEMM_MODE[mode]
     wbytes = L.gcg_gemm_workspace_bytes(int(transA), int(transB), M, N, K, mode, int(split_k))
     ws, wsb = scratch.get(wbytes, A.device)
+    pre = [None, None, None, None]
+    if mode == _lib.GEMM_MODE["tf32x3"]:
+        if a_split is not None and a_split.matches(A, lda):
+            pre[0], pre[1] = C.c_void_p(a_split.hi.data_ptr()), C.c_void_p(a_split.lo.data_ptr())
+        if b_split is not None and b_split.matches(B, ldb):
+            pre[2], pre[3] = C.c_void_p(b_split.hi.data_ptr()), C.c_void_p(b_split.lo.data_ptr())
+    if pre[0] is not None or pre[2] is not None:
+        _lib.check(L.gcg_gemm_presplit_f32(int(transA), int(transB), M, N, K, ap, lda, bp, ldb, cp, ldc, float(beta),
+                                           _vec(bias, "bias"), _lib.act_code(act), mp, ldm, _lib.act_code(mask_act),
+                                           mode, int(split_k), ws, wsb, _stream(), *pre), "gcg_gemm_presplit_f32")
+        return out
     _lib.check(L.gcg_gemm_f32(int(transA), int(transB), M, N, K, ap, lda, bp, ldb, cp, ldc, float(beta),
                               _vec(bias, "bias"), _lib.act_code(act), mp, ldm, _lib.act_code(mask_act), mode,
                               int(split_k), ws, wsb, _stream()), "gcg_gemm_f32")

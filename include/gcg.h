@@ -136,6 +136,17 @@ int gcg_gemm_f32(int transA, int transB, int64_t M, int64_t N, int64_t K,
                  void* stream);
 int64_t gcg_gemm_workspace_bytes(int transA, int transB, int64_t M, int64_t N,
                                  int64_t K, int mode, int32_t split_k);
+/* tf32 hi/lo split of a matrix (the pre-pass of GCG_GEMM_TF32X3): hi = tf32_rn(x), lo = tf32_rn(x - hi),
+ * over n_rows*ld floats (hi / lo have x's leading dimension).  gcg_gemm_presplit_f32 is gcg_gemm_f32 with
+ * operands split beforehand (NULL pair = split inside the call), so that an activation read by several
+ * GEMMs of one training step (H.W, H.W_g, H^T.dZ ...) is split once.  Ignored by the FFMA engine. */
+int gcg_tf32_split_f32(const float* x, int64_t ld, int64_t n_rows, float* hi, float* lo, void* stream);
+int gcg_gemm_presplit_f32(int transA, int transB, int64_t M, int64_t N, int64_t K,
+                          const float* A, int64_t lda, const float* B, int64_t ldb,
+                          float* C, int64_t ldc, float beta, const float* bias, int act,
+                          const float* mask, int64_t ld_mask, int mask_act, int mode,
+                          int32_t split_k, void* workspace, int64_t workspace_bytes, void* stream,
+                          const float* A_hi, const float* A_lo, const float* B_hi, const float* B_lo);
 /* 1 when the tcgen05 engines (GCG_GEMM_TF32X3 / GCG_GEMM_TF32) can run: sm_100 device and
  * a driver that exports cuTensorMapEncodeTiled.  Requests that cannot be described by TMA
  * tensor maps (unaligned base or leading dimension) fall back to the FFMA tiles. */

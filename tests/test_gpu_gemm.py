@@ -118,3 +118,30 @@ def test_tensor_core_engine_is_really_used_and_long_contractions_are_chained():
     assert_close(g1, ref, atol=2e-5 * np.abs(ref).max(), what="tf32x3 weight gradient")
     fma = ops.gemm(Ad, Bd, transA=True, mode="fma").cpu().numpy()
     assert_close(fma, ref, atol=2e-6 * np.abs(ref).max())
+
+
+def test_presplit_operands_give_identical_results():
+    """gcg_gemm_presplit_f32: an operand split once and shared by several GEMMs == splitting inside each call."""
+    from graphconvgeo_b200 import ops
+    if "tf32x3" not in tc_modes():
+        pytest.skip("tcgen05 engine unavailable")
+    rng = np.random.RandomState(9)
+    A = to_dev((rng.standard_normal((3000, 600)) * 0.05).astype(np.float32))
+    B = to_dev((rng.standard_normal((600, 256)) * 0.05).astype(np.float32))
+    D = to_dev((rng.standard_normal((3000, 256)) * 0.05).astype(np.float32))
+    sA, sD = ops.tf32_split(A), ops.tf32_split(D)
+    assert sA.valid and sD.valid
+    n0 = ops.launch_count(reset=True)
+    r1 = ops.gemm(A, B, mode="tf32x3", a_split=sA)
+    assert ops.launch_count(reset=True) == 2            # split of B + tcgen05 kernel; A's split was reused
+    r0 = ops.gemm(A, B, mode="tf32x3")
+    assert ops.launch_count(reset=True) == 3
+    assert torch.equal(r0, r1)
+    t1 = ops.gemm(A, D, transA=True, mode="tf32x3", a_split=sA, b_split=sD)
+    t0 = ops.gemm(A, D, transA=True, mode="tf32x3")
+    assert torch.equal(t0, t1)
+    # a split of a different tensor is ignored, not misused
+    other = ops.tf32_split(to_dev(np.zeros((3000, 600), np.float32)))
+    assert torch.equal(ops.gemm(A, B, mode="tf32x3", a_split=other), r0)
+    # the FFMA engine ignores pre-split operands
+    assert_close(ops.gemm(A, B, mode="fma", a_split=sA).cpu().numpy(), r0.cpu().numpy(), atol=1e-5)
