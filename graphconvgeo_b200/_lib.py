@@ -75,6 +75,7 @@ PROTOTYPES = {
     "gcg_haversine_pairs_f64": (c_int, [c_vp, c_vp, c_i64, c_vp, c_vp]),
     "gcg_csr_transpose_host": (c_int, [c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "gcg_csr_gather_rows_host": (c_i64, [c_i64, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
+    "gcg_csr_split_colblocks_host": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp]),
     "gcg_csr_permute_host": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "gcg_peer_alloc": (c_int, [c_i64, C.POINTER(c_vp), c_vp]),
     "gcg_peer_free": (c_int, [c_vp]),

@@ -227,3 +227,52 @@ extern "C" int gcg_csr_permute_host(int64_t n_rows, const int32_t* indptr, const
   }
   return GCG_OK;
 }
+
+// Column-blocked view of selected rows of a CSR matrix: block b keeps the entries whose column lies in
+// [b*block_cols, (b+1)*block_cols).  Used for X^T.dZ (Dot.grad of lasagne_layers.py:65): the rows of the
+// frequent vocabulary terms are processed one DOCUMENT block at a time, so the gathered block of dZ rows
+// stays L2-resident.  Outputs: out_indptr [n_blocks][n_sel+1] (offsets relative to the block's slice),
+// out_block_off [n_blocks+1] (slice boundaries in out_indices/out_vals), entries grouped by block, row.
+extern "C" int gcg_csr_split_colblocks_host(const int32_t* indptr, const int32_t* indices, const float* vals,
+                                            const int32_t* row_sel, int64_t n_sel, int64_t block_cols,
+                                            int64_t n_blocks, int32_t* out_indptr, int64_t* out_block_off,
+                                            int32_t* out_indices, float* out_vals) {
+  GCG_CHECK_ARG(indptr && indices && vals && row_sel && out_indptr && out_block_off && block_cols > 0 && n_blocks > 0,
+                "gcg_csr_split_colblocks_host: bad argument");
+  const int64_t stride = n_sel + 1;
+  std::vector<int64_t> cnt((size_t)n_blocks * n_sel, 0);
+  for (int64_t i = 0; i < n_sel; ++i) {
+    const int64_t r = row_sel[i];
+    for (int32_t k = indptr[r]; k < indptr[r + 1]; ++k) {
+      const int64_t b = indices[k] / block_cols;
+      if (b >= n_blocks) { set_error("gcg_csr_split_colblocks_host: column %d beyond the last block", indices[k]); return GCG_ERR_SHAPE; }
+      ++cnt[(size_t)b * n_sel + i];
+    }
+  }
+  int64_t total = 0;
+  for (int64_t b = 0; b < n_blocks; ++b) {
+    out_block_off[b] = total;
+    int64_t run = 0;
+    for (int64_t i = 0; i < n_sel; ++i) {
+      out_indptr[b * stride + i] = (int32_t)run;
+      run += cnt[(size_t)b * n_sel + i];
+    }
+    out_indptr[b * stride + n_sel] = (int32_t)run;
+    total += run;
+  }
+  out_block_off[n_blocks] = total;
+  if (!out_indices || !out_vals) return GCG_OK;          // sizing call
+  std::vector<int64_t> cur((size_t)n_blocks * n_sel);
+  for (int64_t b = 0; b < n_blocks; ++b)
+    for (int64_t i = 0; i < n_sel; ++i) cur[(size_t)b * n_sel + i] = out_block_off[b] + out_indptr[b * stride + i];
+  for (int64_t i = 0; i < n_sel; ++i) {
+    const int64_t r = row_sel[i];
+    for (int32_t k = indptr[r]; k < indptr[r + 1]; ++k) {
+      const int64_t b = indices[k] / block_cols;
+      const int64_t dst = cur[(size_t)b * n_sel + i]++;
+      out_indices[dst] = indices[k];
+      out_vals[dst] = vals[k];
+    }
+  }
+  return GCG_OK;
+}

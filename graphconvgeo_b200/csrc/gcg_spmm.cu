@@ -153,6 +153,9 @@ __device__ __forceinline__ void spmm_vec_body(const SpmmArgs& a) {
     beg = __ldg(a.indptr + r);
     end = __ldg(a.indptr + r + 1);
     if (a.only_segments || end - beg > a.long_thresh) return;  // segment blocks + finalize own this row
+    // plain accumulation of an empty row is a no-op: no read-modify-write (column-blocked products
+    // visit every row once per block and most (row, block) pairs are empty)
+    if (beg == end && a.accumulate && !a.bias && a.act == GCG_ACT_IDENTITY && !a.gate) return;
     row = r;
     is_seg = false;
   }

@@ -213,6 +213,23 @@ class DenseLayer(Layer):
         return g
 
 
+def _xt_product(layer, X, dZ, out):
+    """dW = X^T.dZ (Dot.grad of lasagne_layers.py:26,65).  For large X the frequent terms are processed one
+    document block at a time (sparse.BlockedRows) so that the gathered rows of dZ stay in L2."""
+    import os
+    from .sparse import BlockedRows
+    mb = int(os.environ.get("GCG_XT_BLOCK_MB", "64"))      # B200 sweep: 16 MB slower than unblocked, 64 MB best (profiles/r01_spmm_notes.md)
+    big = X.nnz >= (1 << 24) and X.shape[0] * dZ.shape[1] * 4 > (256 << 20)
+    if mb <= 0 or not big:
+        return ops.spmm(X.T, dZ, out=out)
+    key = (id(X), dZ.shape[1], mb)
+    br = getattr(layer, "_xt_blocked", None)
+    if br is None or br[0] != key:
+        br = (key, BlockedRows(X.T, dZ.shape[1], block_mb=mb))
+        layer._xt_blocked = br
+    return br[1].product(dZ, out)
+
+
 def _check_sparse(input):
     # lasagne_layers.py:22-24, 33-35, 61-63
     if not is_sparse(input):
@@ -238,7 +255,7 @@ class SparseInputDenseLayer(DenseLayer):
             ops.act_bwd(grad_output, self._out, self.nonlinearity, out=self._mat("dP", *grad_output.shape))
         if self.b is not None:
             ops.colsum(dP, out=self._grad("b", self.b))
-        ops.spmm(self._X.T, dP, out=self._grad("W", self.W))
+        _xt_product(self, self._X, dP, self._grad("W", self.W))
         return None
 
 
@@ -335,7 +352,7 @@ class SparseConvolutionDenseLayer(_ConvBase):
         if self.b is not None:
             ops.colsum(dP, out=self._grad("b", self.b))
         dZ = ops.spmm(self.H, dP, out=self._operand("Z", *dP.shape))        # A_hat^T = A_hat; Z is dead: reuse
-        ops.spmm(self._X.T, dZ, out=self._grad("W", self.W))                # dW = X^T.dZ
+        _xt_product(self, self._X, dZ, self._grad("W", self.W))             # dW = X^T.dZ
         return None
 
 

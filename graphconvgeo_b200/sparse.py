@@ -231,3 +231,82 @@ def build_ahat_device(indptr, indices, n):
     _lib.check(L.gcg_ahat_fill_device(n, indptr.data_ptr(), indices.data_ptr(), out_ip.data_ptr(), out_ix.data_ptr(),
                                       out_v.data_ptr(), ws.data_ptr(), wsb, stream), "gcg_ahat_fill_device")
     return CSRMatrix(out_ip, out_ix, out_v, (n, n))
+
+
+class BlockedRows:
+    """X^T.dZ with the frequent rows processed one column (document) block at a time.
+
+    ``XT`` is the CSR of X^T [V, N].  Rows with at least ``heavy_factor * n_blocks`` non-zeros ("heavy"
+    vocabulary terms; with Zipf-distributed terms they hold ~90 % of the non-zeros) are cut into
+    ``n_blocks`` column blocks of ``block_cols`` documents (gcg_csr_split_colblocks_host): for one block all
+    heavy rows gather from the same block_cols x F x 4 bytes of dZ, which stay L2-resident, and accumulate
+    into a compact [n_heavy, F] buffer (empty (row, block) pairs are skipped by the kernel).  The light
+    rows are done in one ordinary pass.  Result identical up to summation order inside the heavy rows."""
+
+    def __init__(self, XT: CSRMatrix, F, block_mb=32, heavy_factor=4):
+        ip, ix, d = XT._host_arrays()
+        V, N = XT.shape
+        self.shape = XT.shape
+        self.device = XT.device
+        block_cols = max(1024, int(block_mb * (1 << 20) // (4 * max(F, 1))))
+        self.n_blocks = int(-(-N // block_cols))
+        self.block_cols = block_cols
+        lens = np.diff(ip)
+        heavy = lens >= heavy_factor * self.n_blocks
+        self.heavy_ids = np.flatnonzero(heavy).astype(np.int32)
+        n_sel = len(self.heavy_ids)
+        self.n_heavy = n_sel
+        self.heavy_nnz_fraction = float(lens[heavy].sum()) / max(1, int(lens.sum()))
+        if n_sel == 0 or self.n_blocks <= 1:
+            self.light = XT
+            self.blocks = []
+            return
+        # light rows: heavy rows emptied
+        l_lens = np.where(heavy, 0, lens)
+        l_ip = np.zeros(V + 1, np.int32)
+        np.cumsum(l_lens, out=l_ip[1:])
+        keep = np.repeat(~heavy, lens)
+        self.light = CSRMatrix.from_host((l_ip, np.ascontiguousarray(ix[keep]), np.ascontiguousarray(d[keep])),
+                                         (V, N), self.device, XT.long_row_threshold)
+        del keep
+        L = _lib.lib()
+        nb = self.n_blocks
+        o_ip = np.empty(nb * (n_sel + 1), np.int32)
+        o_off = np.empty(nb + 1, np.int64)
+        _lib.check(L.gcg_csr_split_colblocks_host(_np_ptr(ip), _np_ptr(ix), _np_ptr(d), _np_ptr(self.heavy_ids), n_sel,
+                                                  block_cols, nb, _np_ptr(o_ip), _np_ptr(o_off), None, None),
+                   "gcg_csr_split_colblocks_host")
+        tot = int(o_off[-1])
+        o_ix = np.empty(tot, np.int32)
+        o_d = np.empty(tot, np.float32)
+        _lib.check(L.gcg_csr_split_colblocks_host(_np_ptr(ip), _np_ptr(ix), _np_ptr(d), _np_ptr(self.heavy_ids), n_sel,
+                                                  block_cols, nb, _np_ptr(o_ip), _np_ptr(o_off), _np_ptr(o_ix), _np_ptr(o_d)),
+                   "gcg_csr_split_colblocks_host")
+        dev_ix = torch.from_numpy(o_ix).to(self.device)
+        dev_d = torch.from_numpy(o_d).to(self.device)
+        dev_ip = torch.from_numpy(o_ip).to(self.device)
+        self.blocks = []
+        for b in range(nb):
+            a, e = int(o_off[b]), int(o_off[b + 1])
+            if e == a:
+                continue
+            hip = o_ip[b * (n_sel + 1):(b + 1) * (n_sel + 1)]
+            blk = CSRMatrix(dev_ip[b * (n_sel + 1):(b + 1) * (n_sel + 1)], dev_ix[a:e], dev_d[a:e], (n_sel, N),
+                            host=(hip, None, None), long_row_threshold=XT.long_row_threshold)
+            self.blocks.append(blk)
+        self.heavy_dev = torch.from_numpy(self.heavy_ids.astype(np.int64)).to(self.device)
+        self._tmp = None
+
+    def product(self, dZ, out):
+        """out[V, F] = X^T . dZ"""
+        from . import ops
+        ops.spmm(self.light, dZ, out=out)
+        if not self.blocks:
+            return out
+        F = dZ.shape[1]
+        if self._tmp is None or self._tmp.shape != (self.n_heavy, F):
+            self._tmp = ops.alloc_mat(self.n_heavy, F, dZ.device)
+        for i, blk in enumerate(self.blocks):
+            ops.spmm(blk, dZ, out=self._tmp, accumulate=(i > 0))
+        out.index_copy_(0, self.heavy_dev, self._tmp)      # heavy rows are empty in `light`: plain placement
+        return out

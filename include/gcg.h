@@ -313,6 +313,15 @@ int64_t gcg_csr_gather_rows_host(int64_t n_rows, const int32_t* h_indptr,
                                  const int32_t* idx, int64_t n_idx, int32_t* out_indptr,
                                  int32_t* out_indices, float* out_vals);
 
+/* Column-blocked split of selected rows (document-blocked X^T.dZ, see graphconvgeo_b200/sparse.py
+ * BlockedRows): block b keeps columns [b*block_cols, (b+1)*block_cols).  out_indptr is
+ * [n_blocks][n_sel+1] with offsets relative to the block's slice of out_indices / out_vals, whose
+ * boundaries are out_block_off[n_blocks+1].  Call with out_indices == NULL to size the outputs. */
+int gcg_csr_split_colblocks_host(const int32_t* h_indptr, const int32_t* h_indices, const float* h_vals,
+                                 const int32_t* row_sel, int64_t n_sel, int64_t block_cols, int64_t n_blocks,
+                                 int32_t* out_indptr, int64_t* out_block_off, int32_t* out_indices,
+                                 float* out_vals);
+
 /* Node reordering for gather locality: out = P A Q^T where row i of out is row
  * order[i] of A and column j of A becomes col_map[j] (col_map == NULL keeps the
  * columns); columns are re-sorted inside every row.  The GCN is permutation

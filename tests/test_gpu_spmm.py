@@ -201,3 +201,28 @@ def test_full_size_properties_twitter_world_shape():
     # panel-major execution and the bulk-copy staged kernel give the same bits as whole-row execution
     assert torch.equal(ops.spmm(Ad, x, panel_cols=16), ax)
     assert torch.equal(ops.spmm(Ad, x, panel_cols=-1), ops.spmm(Ad, x, panel_cols=0))
+
+
+def test_document_blocked_transpose_product_matches_plain():
+    """sparse.BlockedRows: heavy rows of X^T processed per column block with accumulation == one plain SpMM."""
+    from graphconvgeo_b200 import ops
+    from graphconvgeo_b200.sparse import BlockedRows, CSRMatrix
+    rng = np.random.RandomState(11)
+    light = random_csr(rng, 400, 6000, 3)
+    heavy = sp.random(12, 6000, density=0.4, format="csr", dtype=np.float32, random_state=rng)
+    XT = sp.vstack([light[:200], heavy, light[200:]]).tocsr()
+    XT.sort_indices()
+    D = (rng.standard_normal((6000, 96)) * 0.1).astype(np.float32)
+    Xd = CSRMatrix.from_scipy(XT)
+    br = BlockedRows(Xd, F=96, block_mb=0)          # block_cols = 1024 -> 6 column blocks
+    assert br.n_blocks == 6 and br.n_heavy >= 12 and len(br.blocks) == 6
+    out = ops.alloc_mat(XT.shape[0], 96, "cuda")
+    out.fill_(123.0)
+    br.product(to_dev(D), out)
+    ref = np.asarray(XT @ D, dtype=np.float32)
+    got = out.cpu().numpy()
+    lightrows = np.ones(XT.shape[0], bool)
+    lightrows[br.heavy_ids] = False
+    assert np.array_equal(got[lightrows], ref[lightrows])          # light rows: same kernel, same order
+    assert_close(got[~lightrows], ref[~lightrows], atol=2e-5)      # heavy rows: block-wise summation order
+    assert np.array_equal(got, br.product(to_dev(D), ops.alloc_mat(XT.shape[0], 96, "cuda")).cpu().numpy())
