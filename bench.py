@@ -421,10 +421,14 @@ def spmm_roofline(m, wl, dev, reps=10):
             ts.append(s.elapsed_time(e))
         results[label] = float(np.mean(ts))
     t_ms = results["auto"]
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tp) and not dist_mode:
+        traffic = json.load(open(tp)).get(wl.name)
     achieved = alg_bytes / (t_ms * 1e-3) / 1e9
     gather_model = (8 * nnz + 4 * nnz * F + 4 * N * F) / (t_ms * 1e-3) / 1e9
     return {"roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "spmm_vec_kernel (A_hat.H, F=%d%s)" % (F, ", local rows incl. NCCL all-gather of H" if dist_mode else ""),
+                         "traffic": traffic, "kernel": "spmm_vec_kernel (A_hat.H, F=%d%s)" % (F, ", local rows incl. NCCL all-gather of H" if dist_mode else ""),
                          "algorithmic_bytes": alg_bytes, "ms": t_ms, "peak_source": peak_src,
                          "frac_of_nominal_8000": achieved / 8000.0},
             "detail": {"N": N, "F": F, "nnz": nnz, "ms_auto_panel": results["auto"], "ms_whole_rows": results.get("rows"),
