@@ -21,7 +21,7 @@ OBJ = os.path.join(HERE, "_obj")
 LIB = os.path.join(HERE, "libgcg.so")
 
 SOURCES = ["gcg_core.cu", "gcg_spmm.cu", "gcg_gemm.cu", "gcg_gemm_tc.cu", "gcg_elementwise.cu",
-           "gcg_graph.cu", "gcg_host.cpp", "gcg_peer.cu"]
+           "gcg_graph.cu", "gcg_host.cpp", "gcg_peer.cu", "gcg_spgemm.cu"]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-O3,-Wall,-fopenmp", "--expt-relaxed-constexpr",

@@ -189,10 +189,39 @@ class DenseLayer(Layer):
         return (input_shape[0], self.num_units)
 
     def get_output_for(self, input, **kwargs):
-        if self.nonlinearity == "softmax":
-            raise NotImplementedError("dense softmax head is outside the GCN hot path")
-        return ops.gemm(input, self.W, bias=self.b, act=self.nonlinearity,
-                        out=self._mat("out", input.shape[0], self.num_units))
+        """act(input.W + b).  A softmax layer (the MLP head, mlp.py:183-185) returns probabilities, or
+        the logits with ``logits=True`` (the training step feeds them to the fused softmax/CE head)."""
+        n = input.shape[0]
+        self._in = input
+        fused_act = "identity" if self.nonlinearity == "softmax" else self.nonlinearity
+        out = ops.gemm(input, self.W, bias=self.b, act=fused_act, out=self._mat(("out", n), n, self.num_units))
+        self._out = out
+        return self._softmax_or(out, kwargs)
+
+    def _softmax_or(self, out, kwargs):
+        if self.nonlinearity == "softmax" and not kwargs.get("logits", False):
+            n = out.shape[0]
+            probs = self._mat(("probs", n), n, self.num_units)
+            ops.softmax_ce(out, probs=probs)
+            return probs
+        return out
+
+    def backward(self, grad_output, preact=False, input_mask=None, need_input_grad=True, **kwargs):
+        """T.dot's gradients: dW = in^T.dP, db = colsum(dP), d(in) = dP.W^T.  ``grad_output`` is the grad wrt
+        the LOGITS for a softmax layer; ``input_mask=(A_prev, act)`` fuses the previous layer's act'."""
+        n = grad_output.shape[0]
+        if preact or self.nonlinearity in ("softmax", "identity"):
+            dP = grad_output
+        else:
+            dP = ops.act_bwd(grad_output, self._out, self.nonlinearity, out=self._mat(("dP", n), n, self.num_units))
+        if self.b is not None:
+            ops.colsum(dP, out=self._grad("b", self.b))
+        ops.gemm(self._in, dP, transA=True, out=self._grad("W", self.W))
+        if not need_input_grad:
+            return None
+        mk, mact = (None, "identity") if input_mask is None else input_mask
+        return ops.gemm(dP, self.W, transB=True, mask=mk, mask_act=mact,
+                        out=self._mat(("dIn", n), n, self.num_inputs))
 
     def _split(self, key, t, other_dim):
         """tf32 hi/lo split of an activation that several tcgen05 GEMMs of this step read (None when the
@@ -243,16 +272,19 @@ class SparseInputDenseLayer(DenseLayer):
         _check_sparse(input)
         X = as_csr(input, self.device)
         self._X = X
-        out = ops.spmm(X, self.W, bias=self.b, act=self.nonlinearity,
-                       out=self._mat("out", X.shape[0], self.num_units))     # :26-29
+        n = X.shape[0]
+        fused_act = "identity" if self.nonlinearity == "softmax" else self.nonlinearity
+        out = ops.spmm(X, self.W, bias=self.b, act=fused_act,
+                       out=self._mat(("out", n), n, self.num_units))         # :26-29
         self._out = out
-        return out
+        return self._softmax_or(out, kwargs)
 
     def backward(self, grad_output, preact=False, **kwargs):
         """grad wrt the activation output (or the pre-activation when ``preact``).
         dW = X^T.dP (Dot.grad), db = colsum(dP).  X is an input: no grad is returned."""
-        dP = grad_output if preact or self.nonlinearity == "identity" else \
-            ops.act_bwd(grad_output, self._out, self.nonlinearity, out=self._mat("dP", *grad_output.shape))
+        n = grad_output.shape[0]
+        dP = grad_output if preact or self.nonlinearity in ("identity", "softmax") else \
+            ops.act_bwd(grad_output, self._out, self.nonlinearity, out=self._mat(("dP", n), n, self.num_units))
         if self.b is not None:
             ops.colsum(dP, out=self._grad("b", self.b))
         _xt_product(self, self._X, dP, self._grad("W", self.W))
@@ -278,7 +310,10 @@ class SparseInputDropoutLayer(Layer):
         retain = 1.0 - self.p
         keep = (torch.rand(X.data.shape, device=X.data.device) < retain).to(torch.float32)
         data = X.data * keep * ((1.0 / retain) if self.rescale else 1.0)      # :44-52
-        return CSRMatrix(X.indptr, X.indices, data, X.shape, long_row_threshold=X.long_row_threshold)
+        host = None if X.host is None else (X.host[0], None, None)       # same pattern: the row offsets stay valid
+        out = CSRMatrix(X.indptr, X.indices, data, X.shape, host=host, long_row_threshold=X.long_row_threshold)
+        out.device_built = X.device_built
+        return out
 
 
 class TargetIndices:

@@ -42,15 +42,16 @@ class CSRMatrix:
         self.long_row_threshold = int(long_row_threshold)
         self._plan = None
         self._T = None
+        self.device_built = False     # True: no host copy of indices/data exists (device-sliced minibatch)
         assert indptr.dtype == torch.int32 and indices.dtype == torch.int32 and data.dtype == torch.float32
         assert indptr.numel() == self.shape[0] + 1
 
     # ------------------------------------------------------------------ ctor
     @classmethod
-    def from_scipy(cls, m, device="cuda", long_row_threshold=256):
+    def from_scipy(cls, m, device="cuda", long_row_threshold=256, sort_indices=True):
         import scipy.sparse as sp
         m = sp.csr_matrix(m)
-        if not m.has_sorted_indices:
+        if sort_indices and not m.has_sorted_indices:
             m = m.copy()
             m.sort_indices()
         if m.nnz >= 2 ** 31 - 1:
@@ -81,7 +82,7 @@ class CSRMatrix:
         return self
 
     def _host_arrays(self):
-        if self.host is None:
+        if self.host is None or self.host[1] is None:
             self.host = (self.indptr.cpu().numpy(), self.indices.cpu().numpy(), self.data.cpu().numpy())
         return self.host
 
@@ -124,7 +125,10 @@ class CSRMatrix:
     # ------------------------------------------------- one-off host helpers
     @property
     def T(self):
-        """CSR of the transpose (stable), built once on the host (gcg_csr_transpose_host)."""
+        """CSR of the transpose (stable), built once on the host (gcg_csr_transpose_host); matrices
+        sliced on the device (minibatches) are transposed there (gcg_csr_transpose_device)."""
+        if self._T is None and self.device_built:
+            return self.transpose_device()
         if self._T is None:
             ip, ix, d = self._host_arrays()
             n, m = self.shape
@@ -156,6 +160,55 @@ class CSRMatrix:
         return CSRMatrix.from_host((oip, oix, od), (len(idx), self.shape[1]), self.device,
                                    self.long_row_threshold)
 
+    # ------------------------------------------------ device-side minibatch helpers
+    def gather_rows_device(self, rows):
+        """A[rows, :] built on the GPU (gcg_csr_gather_rows_device) -- `inputs[excerpt]` of
+        iterate_minibatches (mlp.py:81-91).  ``rows``: host int array; entry order inside rows is kept."""
+        rows = np.ascontiguousarray(np.asarray(rows), dtype=np.int32)
+        if self.host is None:
+            self.host = (self.indptr.cpu().numpy(), None, None)
+        ip = self.host[0]
+        lens = (ip[1:] - ip[:-1])[rows]
+        oip = np.zeros(len(rows) + 1, np.int64)
+        np.cumsum(lens, out=oip[1:])
+        nnz = int(oip[-1])
+        if nnz >= 2 ** 31 - 1:
+            raise ValueError("gathered rows do not fit int32 CSR offsets")
+        oip = oip.astype(np.int32)
+        dev = self.device
+        d_rows = torch.from_numpy(rows).to(dev)
+        d_oip = torch.from_numpy(oip).to(dev)
+        oix = torch.empty(nnz, dtype=torch.int32, device=dev)
+        od = torch.empty(nnz, dtype=torch.float32, device=dev)
+        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(_lib.lib().gcg_csr_gather_rows_device(self.indptr.data_ptr(), self.indices.data_ptr(),
+                                                         self.data.data_ptr(), d_rows.data_ptr(), len(rows),
+                                                         d_oip.data_ptr(), oix.data_ptr(), od.data_ptr(), stream),
+                   "gcg_csr_gather_rows_device")
+        out = CSRMatrix(d_oip, oix, od, (len(rows), self.shape[1]), host=(oip, None, None),
+                        long_row_threshold=self.long_row_threshold)
+        out.device_built = True           # no host copy of indices/data: transposes happen on the device too
+        return out
+
+    def transpose_device(self):
+        """Stable CSR transpose on the GPU (gcg_csr_transpose_device); cached like ``T``."""
+        if self._T is None:
+            n, m = self.shape
+            dev = self.device
+            L = _lib.lib()
+            nnz = self.nnz
+            wsb = int(L.gcg_csr_transpose_device_workspace_bytes(n, m, nnz))
+            ws = torch.empty(wsb + 256, dtype=torch.uint8, device=dev)
+            off = (-ws.data_ptr()) % 256
+            tip = torch.empty(m + 1, dtype=torch.int32, device=dev)
+            tix = torch.empty(nnz, dtype=torch.int32, device=dev)
+            td = torch.empty(nnz, dtype=torch.float32, device=dev)
+            stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            _lib.check(L.gcg_csr_transpose_device(n, m, nnz, self.indptr.data_ptr(), self.indices.data_ptr(),
+                                                  self.data.data_ptr(), tip.data_ptr(), tix.data_ptr(), td.data_ptr(),
+                                                  ws.data_ptr() + off, wsb, stream), "gcg_csr_transpose_device")
+            self._T = CSRMatrix(tip, tix, td, (m, n), long_row_threshold=self.long_row_threshold)
+        return self._T
 
     def permute(self, order, col_map=None):
         """P A Q^T: row i of the result is row order[i]; column j becomes col_map[j]
@@ -231,6 +284,54 @@ def build_ahat_device(indptr, indices, n):
     _lib.check(L.gcg_ahat_fill_device(n, indptr.data_ptr(), indices.data_ptr(), out_ip.data_ptr(), out_ix.data_ptr(),
                                       out_v.data_ptr(), ws.data_ptr(), wsb, stream), "gcg_ahat_fill_device")
     return CSRMatrix(out_ip, out_ix, out_v, (n, n))
+
+
+def spgemm(A: "CSRMatrix", B: "CSRMatrix", a_values=None) -> "CSRMatrix":
+    """C = A * B for two device CSR matrices, every entry summed in scipy's csr_matmat order, rows emitted
+    with ascending columns (gcg_spgemm_count_csr / gcg_spgemm_fill_csr_f32).  ``a_values``: optional float64 device tensor replacing A.data -- the reference
+    multiplies a FLOAT64 A_hat into X (main.py:522-530): float64 sums, one float32 rounding.  With float32
+    values the sums are float32, scipy's rule for float32 * float32."""
+    if A.shape[1] != B.shape[0]:
+        raise ValueError("spgemm: A is %s but B is %s" % (A.shape, B.shape))
+    dev = A.device
+    L = _lib.lib()
+    n, V = A.shape[0], B.shape[1]
+    av = A.data if a_values is None else a_values
+    if av.dtype not in (torch.float32, torch.float64) or av.numel() != A.nnz or not av.is_contiguous():
+        raise TypeError("spgemm: a_values must be a contiguous float32/float64 tensor with A.nnz elements")
+    stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    wsb = int(L.gcg_spgemm_workspace_bytes(V))
+    ws = torch.empty(wsb + 256, dtype=torch.uint8, device=dev)
+    wp = ws.data_ptr() + (-ws.data_ptr()) % 256
+    row_nnz = torch.zeros(max(n, 1), dtype=torch.int32, device=dev)
+    _lib.check(L.gcg_spgemm_count_csr(n, V, A.indptr.data_ptr(), A.indices.data_ptr(), B.indptr.data_ptr(),
+                                      B.indices.data_ptr(), row_nnz.data_ptr(), wp, wsb, stream),
+               "gcg_spgemm_count_csr")
+    c_ip = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+    torch.cumsum(row_nnz[:n], 0, out=c_ip[1:])
+    nnz = int(c_ip[-1].item())
+    if nnz >= 2 ** 31 - 1:
+        raise _lib.GcgError("spgemm: the product has %d non-zeros; split A into row blocks (int32 CSR offsets)" % nnz)
+    c_ix = torch.empty(nnz, dtype=torch.int32, device=dev)
+    c_d = torch.empty(nnz, dtype=torch.float32, device=dev)
+    _lib.check(L.gcg_spgemm_fill_csr_f32(n, V, A.indptr.data_ptr(), A.indices.data_ptr(), av.data_ptr(),
+                                         int(av.dtype == torch.float64), B.indptr.data_ptr(), B.indices.data_ptr(),
+                                         B.data.data_ptr(), c_ip.data_ptr(), c_ix.data_ptr(), c_d.data_ptr(), wp, wsb,
+                                         stream), "gcg_spgemm_fill_csr_f32")
+    return CSRMatrix(c_ip.to(torch.int32), c_ix, c_d, (n, V))
+
+
+def smooth_features(H, X, device="cuda") -> "CSRMatrix":
+    """`X_conv = H * X; X_conv = X_conv.tocsr().astype('float32')` (main.py:528-530, tensormain.py:112-114).
+    ``H``: scipy sparse A_hat (float64 as the reference builds it, or float32); ``X``: scipy CSR / CSRMatrix."""
+    import scipy.sparse as sp
+    Hs = sp.csr_matrix(H)
+    A = CSRMatrix.from_scipy(Hs, device=device, sort_indices=False)
+    a_vals = None
+    if Hs.dtype == np.float64:
+        a_vals = torch.from_numpy(np.ascontiguousarray(Hs.data)).to(A.device)
+    B = X if isinstance(X, CSRMatrix) else CSRMatrix.from_scipy(X, device=device, sort_indices=False)
+    return spgemm(A, B, a_values=a_vals)
 
 
 class BlockedRows:

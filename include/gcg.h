@@ -332,6 +332,50 @@ int gcg_csr_permute_host(int64_t n_rows, const int32_t* h_indptr, const int32_t*
                          const float* h_vals, const int32_t* order, const int32_t* col_map,
                          int32_t* out_indptr, int32_t* out_indices, float* out_vals);
 
+/* ------------------------------------------- input smoothing + minibatches */
+/* One-shot smoothing X_conv = A_hat * X (sparse x sparse) -- main.py:528-530,
+ * tensormain.py:112-114: `X_conv = H * X; X_conv = X_conv.tocsr().astype('float32')`.
+ * There H is FLOAT64 and X float32, so scipy's csr_matmat accumulates every output entry in
+ * float64, in the order the rows j of A's row i are visited (CSR order); the result is rounded to
+ * float32 once and -- because scipy's astype() canonicalises -- ends up with ascending columns in every
+ * row.  The two kernels reproduce exactly that: one warp per output row, A's entries strictly in stored
+ * order, the 32 lanes over the entries of B's row j, a per-warp dense accumulator plus a bitmap of touched
+ * columns (workspace), then one sweep of the bitmap emits the row in ascending column order.  Values are
+ * bit-identical to scipy.  Differences: entries whose sum is exactly 0.0 are kept (scipy's csr_matmat
+ * drops them); B must not hold duplicate column entries inside a row.
+ *
+ * Protocol: (1) gcg_spgemm_count_csr -> row_nnz[n_rows]; (2) caller builds c_indptr
+ * (int64[n_rows+1], exclusive scan) and allocates c_indices / c_vals; (3) gcg_spgemm_fill_csr_f32.
+ * a_vals is float64 when a_is_f64 != 0 (float64 sums, the reference's case), else float32 (float32
+ * sums, scipy's promotion rule for float32 * float32).
+ * Workspace: gcg_spgemm_workspace_bytes(n_cols_b); zero-initialised by the calls themselves. */
+int64_t gcg_spgemm_workspace_bytes(int64_t n_cols_b);
+int gcg_spgemm_count_csr(int64_t n_rows, int64_t n_cols_b, const int32_t* a_indptr, const int32_t* a_indices,
+                         const int32_t* b_indptr, const int32_t* b_indices, int32_t* row_nnz,
+                         void* workspace, int64_t workspace_bytes, void* stream);
+int gcg_spgemm_fill_csr_f32(int64_t n_rows, int64_t n_cols_b, const int32_t* a_indptr, const int32_t* a_indices,
+                            const void* a_vals, int a_is_f64, const int32_t* b_indptr, const int32_t* b_indices,
+                            const float* b_vals, const int64_t* c_indptr, int32_t* c_indices, float* c_vals,
+                            void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Device-side minibatch slicing, `inputs[excerpt]` of iterate_minibatches (mlp.py:81-91):
+ * out CSR = rows d_rows[0..n_sel) of the input CSR, entry order inside a row preserved.
+ * out_indptr (int32[n_sel+1], the exclusive scan of the selected rows' lengths) is supplied by the
+ * caller; indptr / out_indptr may hold absolute offsets into indices / out_indices. */
+int gcg_csr_gather_rows_device(const int32_t* d_indptr, const int32_t* d_indices, const float* d_vals,
+                               const int32_t* d_rows, int64_t n_sel, const int32_t* d_out_indptr,
+                               int32_t* d_out_indices, float* d_out_vals, void* stream);
+
+/* Device-side stable CSR transpose (rows ascending inside each output row) of a [n_rows, n_cols]
+ * matrix with nnz entries starting at d_indptr[0]; gives X_batch^T for dW = X_batch^T.dP
+ * (Dot.grad of lasagne_layers.py:26) without a host round trip.  Uses a radix sort (CUB) on the
+ * column index.  Workspace: gcg_csr_transpose_device_workspace_bytes(n_rows, n_cols, nnz). */
+int64_t gcg_csr_transpose_device_workspace_bytes(int64_t n_rows, int64_t n_cols, int64_t nnz);
+int gcg_csr_transpose_device(int64_t n_rows, int64_t n_cols, int64_t nnz, const int32_t* d_indptr,
+                             const int32_t* d_indices, const float* d_vals, int32_t* t_indptr,
+                             int32_t* t_indices, float* t_vals, void* workspace, int64_t workspace_bytes,
+                             void* stream);
+
 #ifdef __cplusplus
 }
 #endif
