@@ -125,6 +125,25 @@ def cpu_reference_epoch(workload, n_layers, highway, scale, epochs=1, threads=No
 CPU_SCALE = {"twitter-world": 1.0 / 64, "twitter-us": 1.0 / 24, "geotext": 1.0, "tiny": 1.0}
 
 
+def cpu_mlp_epoch(Xc_host, y_train, hidden, n_classes, batch, n_batches, sample_batches=4):
+    """cpu_baseline of the minibatch MLP (used by scripts/smooth_bench.py): the NumPy
+    port of mlp.py:267-271 timed on ``sample_batches`` minibatches, scaled to one epoch.  Returns ms."""
+    from oracle import mlp_oracle as mo
+    params = mo.init_params(np.random.RandomState(0), Xc_host.shape[1], hidden, n_classes)
+    net = mo.MLPOracle((1e-6, 1e-6))
+    rng = np.random.RandomState(0)
+    st = mo.AdamState(params)
+    sample_batches = max(1, min(n_batches, sample_batches))
+    t0 = time.perf_counter()
+    for k, idx in enumerate(mo.iterate_minibatches(Xc_host.shape[0], batch, rng)):
+        if k == sample_batches:
+            break
+        _, _, grads = net.loss_and_grads(params, Xc_host[idx], y_train[idx])
+        mo.adam_step(params, grads, st, lr=2e-3)
+    per_batch = (time.perf_counter() - t0) / sample_batches
+    return per_batch * n_batches * 1e3, sample_batches
+
+
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path (oracle port; Theano is not
     installable here) on the box's host cores, bounded sample, same metric/unit/config."""

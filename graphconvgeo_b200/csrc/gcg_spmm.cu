@@ -22,6 +22,8 @@
 //     caller sizes to stay resident in the 126 MB L2 (evict_last on gathers).
 //   * Epilogue fused: +bias, relu/tanh/sigmoid, highway mix g*Hc + (1-g)*H.
 #include <algorithm>
+#include <map>
+#include <mutex>
 #include <vector>
 
 #include "gcg_common.cuh"
@@ -37,7 +39,54 @@ struct gcg_plan {
   int32_t* d_seg_beg;      // [n_seg]
   int32_t* d_long_rows;    // [n_long]
   int32_t* d_long_segptr;  // [n_long+1]
+  void* d_block;           // one pooled allocation holding the four arrays above
+  size_t block_cap;
+  int device;
 };
+
+// Plans of minibatch matrices are created and destroyed thousands of times per fit; cudaMalloc / cudaFree
+// cost ~1 ms each (and much more on a busy driver), so the long-row tables come from a small size-bucketed
+// cache of device blocks that are only returned to the driver when the cache is full.
+namespace {
+struct PlanBlockCache {
+  std::mutex mu;
+  std::multimap<std::pair<int, size_t>, void*> free_blocks;   // (device, capacity) -> block
+  size_t cached_bytes = 0;
+  static constexpr size_t kMaxCached = 256u << 20;
+} g_plan_blocks;
+
+size_t plan_block_capacity(size_t bytes) {
+  size_t cap = 4096;
+  while (cap < bytes) cap <<= 1;
+  return cap;
+}
+
+cudaError_t plan_block_acquire(int device, size_t cap, void** out) {
+  {
+    std::lock_guard<std::mutex> lk(g_plan_blocks.mu);
+    auto it = g_plan_blocks.free_blocks.find({device, cap});
+    if (it != g_plan_blocks.free_blocks.end()) {
+      *out = it->second;
+      g_plan_blocks.free_blocks.erase(it);
+      g_plan_blocks.cached_bytes -= cap;
+      return cudaSuccess;
+    }
+  }
+  return cudaMalloc(out, cap);
+}
+
+void plan_block_release(int device, size_t cap, void* p) {
+  {
+    std::lock_guard<std::mutex> lk(g_plan_blocks.mu);
+    if (g_plan_blocks.cached_bytes + cap <= PlanBlockCache::kMaxCached) {
+      g_plan_blocks.free_blocks.insert({{device, cap}, p});
+      g_plan_blocks.cached_bytes += cap;
+      return;
+    }
+  }
+  cudaFree(p);
+}
+}  // namespace
 
 namespace gcg {
 
@@ -497,21 +546,33 @@ extern "C" int gcg_plan_create_csr(int64_t n_rows, int64_t n_cols, int64_t nnz,
   p->n_seg = (int64_t)seg_row.size();
   p->max_deg = max_deg;
   p->d_seg_row = p->d_seg_beg = p->d_long_rows = p->d_long_segptr = nullptr;
+  p->d_block = nullptr;
+  p->block_cap = 0;
+  p->device = 0;
   if (p->n_long > 0) {
-    auto up = [](int32_t** dst, const std::vector<int32_t>& v) -> cudaError_t {
-      cudaError_t e = cudaMalloc(dst, sizeof(int32_t) * v.size());
-      if (e != cudaSuccess) return e;
-      return cudaMemcpy(*dst, v.data(), sizeof(int32_t) * v.size(), cudaMemcpyHostToDevice);
-    };
-    cudaError_t e = up(&p->d_seg_row, seg_row);
-    if (e == cudaSuccess) e = up(&p->d_seg_beg, seg_beg);
-    if (e == cudaSuccess) e = up(&p->d_long_rows, long_rows);
-    if (e == cudaSuccess) e = up(&p->d_long_segptr, long_segptr);
+    // one block, one upload: [seg_row | seg_beg | long_rows | long_segptr]
+    std::vector<int32_t> packed;
+    packed.reserve(2 * seg_row.size() + 2 * long_rows.size() + 1);
+    packed.insert(packed.end(), seg_row.begin(), seg_row.end());
+    packed.insert(packed.end(), seg_beg.begin(), seg_beg.end());
+    packed.insert(packed.end(), long_rows.begin(), long_rows.end());
+    packed.insert(packed.end(), long_segptr.begin(), long_segptr.end());
+    const size_t bytes = packed.size() * sizeof(int32_t);
+    cudaError_t e = cudaGetDevice(&p->device);
+    p->block_cap = plan_block_capacity(bytes);
+    if (e == cudaSuccess) e = plan_block_acquire(p->device, p->block_cap, &p->d_block);
+    // synchronous copy: also orders the upload after any kernel of a previous owner of the block
+    if (e == cudaSuccess) e = cudaMemcpy(p->d_block, packed.data(), bytes, cudaMemcpyHostToDevice);
     if (e != cudaSuccess) {
       set_error("gcg_plan_create_csr: %s", cudaGetErrorString(e));
       gcg_plan_destroy(p);
       return GCG_ERR_CUDA;
     }
+    int32_t* base = reinterpret_cast<int32_t*>(p->d_block);
+    p->d_seg_row = base;
+    p->d_seg_beg = base + seg_row.size();
+    p->d_long_rows = base + 2 * seg_row.size();
+    p->d_long_segptr = base + 2 * seg_row.size() + long_rows.size();
   }
   *out = p;
   return GCG_OK;
@@ -519,10 +580,11 @@ extern "C" int gcg_plan_create_csr(int64_t n_rows, int64_t n_cols, int64_t nnz,
 
 extern "C" int gcg_plan_destroy(gcg_plan* p) {
   if (!p) return GCG_OK;
-  cudaFree(p->d_seg_row);
-  cudaFree(p->d_seg_beg);
-  cudaFree(p->d_long_rows);
-  cudaFree(p->d_long_segptr);
+  if (p->d_block) {
+    // kernels still reading the tables (on any stream) must finish before the block can serve another plan
+    cudaDeviceSynchronize();
+    plan_block_release(p->device, p->block_cap, p->d_block);
+  }
   delete p;
   return GCG_OK;
 }

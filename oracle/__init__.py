@@ -14,6 +14,11 @@ Parity status (see DESIGN.md "Oracle"):
   function cites file:line) and is cross-checked against torch-CPU autograd.
 * Highway gate: **parity unpinned** -- the gate is not in the reference at all;
   the oracle restates the formula given in BASELINE.json's ``north_star``.
+* Input smoothing ``X_conv = H * X`` (``mlp_oracle.smooth_features``): **pinned** -- the
+  function calls scipy's ``csr_matmat`` + ``astype`` exactly as main.py:528-530 does, i.e. it
+  executes the reference's own third-party routine; the CUDA SpGEMM is compared bit for bit.
+  The minibatch MLP around it (``mlp_oracle.MLPOracle`` / ``fit``, mlp.py:121-314) is
+  **unpinned** like the GCN and cross-checked against torch-CPU autograd.
 * kd-tree labels (``kdtree_oracle.py``): **pinned** -- checked bit-for-bit
   against the reference's own ``kdtree.py`` (imported from /root/reference by
   ``tests/golden/make_kdtree_golden.py``, outputs committed under
