@@ -59,6 +59,8 @@ struct SpgemmArgs {
   double* acc;
   int64_t vpad;
   int n_rows;
+  int drop_diagonal;   // skip column == row (graph projection: no self edges)
+  int pattern_only;    // NUMERIC pass without values (c_vals == NULL)
 };
 
 __device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
@@ -98,7 +100,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) spgemm_rows_kernel(SpgemmAr
     for (int p = pb; p < pe; ++p) {
       const int j = a.a_indices[p];
       AT av = AT(0);
-      if (NUMERIC) av = a_vals[p];
+      if (NUMERIC && !a.pattern_only) av = a_vals[p];
       const int qb = a.b_indptr[j], qe = a.b_indptr[j + 1];
       for (int q0 = qb; q0 < qe; q0 += 32) {
         const int q = q0 + lane;
@@ -107,7 +109,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) spgemm_rows_kernel(SpgemmAr
           kmin = min(kmin, k);
           kmax = max(kmax, k);
           atomicOr(&bitmap[k >> 5], 1u << (k & 31));
-          if (NUMERIC) acc[k] = add_rn(acc[k], mul_rn(av, (AT)a.b_vals[q]));   // sums[k] += v * Bx[kk]
+          if (NUMERIC && !a.pattern_only) acc[k] = add_rn(acc[k], mul_rn(av, (AT)a.b_vals[q]));   // sums[k] += v * Bx[kk]
         }
         __syncwarp();   // the next chunk may touch the same columns from other lanes
       }
@@ -129,6 +131,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) spgemm_rows_kernel(SpgemmAr
       for (int w0 = kmin >> 5; w0 <= w_end; w0 += 32) {
         const int w = w0 + lane;
         uint32_t bits = (w <= w_end) ? __ldcg(&bitmap[w]) : 0u;   // set by atomics at L2: do not trust L1
+        if (bits) bitmap[w] = 0u;
+        if (a.drop_diagonal && w == (row >> 5)) bits &= ~(1u << (row & 31));
         const int c = __popc(bits);
         int incl = c;
 #pragma unroll
@@ -136,19 +140,18 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) spgemm_rows_kernel(SpgemmAr
           const int t = __shfl_up_sync(0xffffffffu, incl, o);
           if (lane >= o) incl += t;
         }
-        if (bits) {
-          bitmap[w] = 0u;
-          if (NUMERIC) {
-            int pos = cnt + incl - c;
-            while (bits) {
-              const int bpos = __ffs(bits) - 1;
-              bits &= bits - 1;
-              const int k = (w << 5) + bpos;
-              out_idx[pos] = k;
+        if (NUMERIC && bits) {
+          int pos = cnt + incl - c;
+          while (bits) {
+            const int bpos = __ffs(bits) - 1;
+            bits &= bits - 1;
+            const int k = (w << 5) + bpos;
+            out_idx[pos] = k;
+            if (!a.pattern_only) {
               out_val[pos] = (float)acc[k];
               acc[k] = AT(0);
-              ++pos;
             }
+            ++pos;
           }
         }
         cnt += __shfl_sync(0xffffffffu, incl, 31);
@@ -251,7 +254,7 @@ static int spgemm_common(bool numeric, int64_t n_rows, int64_t n_cols_b, SpgemmA
   a.vpad = L.vpad;
   a.n_rows = (int)n_rows;
   // row counter, bitmaps and (numeric pass) accumulators start at zero; the kernel leaves them zero
-  GCG_CUDA(cudaMemsetAsync(ws, 0, (size_t)(numeric ? L.total : L.acc_off), st));
+  GCG_CUDA(cudaMemsetAsync(ws, 0, (size_t)((numeric && !a.pattern_only) ? L.total : L.acc_off), st));
   const unsigned grid = (unsigned)(L.workers / kWarpsPerCta);
   if (!numeric)
     spgemm_rows_kernel<false, float><<<grid, kWarpsPerCta * 32, 0, st>>>(a);
@@ -265,13 +268,30 @@ static int spgemm_common(bool numeric, int64_t n_rows, int64_t n_cols_b, SpgemmA
 
 extern "C" int gcg_spgemm_count_csr(int64_t n_rows, int64_t n_cols_b, const int32_t* a_indptr,
                                     const int32_t* a_indices, const int32_t* b_indptr, const int32_t* b_indices,
-                                    int32_t* row_nnz, void* workspace, int64_t workspace_bytes, void* stream) {
+                                    int drop_diagonal, int32_t* row_nnz, void* workspace, int64_t workspace_bytes,
+                                    void* stream) {
   GCG_CHECK_ARG(row_nnz || n_rows == 0, "gcg_spgemm_count_csr: row_nnz is NULL");
   SpgemmArgs a{};
   a.a_indptr = a_indptr; a.a_indices = a_indices;
   a.b_indptr = b_indptr; a.b_indices = b_indices;
   a.row_nnz = row_nnz;
+  a.drop_diagonal = drop_diagonal ? 1 : 0;
   return spgemm_common(false, n_rows, n_cols_b, a, 0, workspace, workspace_bytes, stream);
+}
+
+extern "C" int gcg_spgemm_fill_pattern_csr(int64_t n_rows, int64_t n_cols_b, const int32_t* a_indptr,
+                                           const int32_t* a_indices, const int32_t* b_indptr,
+                                           const int32_t* b_indices, int drop_diagonal, const int64_t* c_indptr,
+                                           int32_t* c_indices, void* workspace, int64_t workspace_bytes,
+                                           void* stream) {
+  GCG_CHECK_ARG(c_indptr, "gcg_spgemm_fill_pattern_csr: c_indptr is NULL");
+  SpgemmArgs a{};
+  a.a_indptr = a_indptr; a.a_indices = a_indices;
+  a.b_indptr = b_indptr; a.b_indices = b_indices;
+  a.c_indptr = c_indptr; a.c_indices = c_indices;
+  a.drop_diagonal = drop_diagonal ? 1 : 0;
+  a.pattern_only = 1;
+  return spgemm_common(true, n_rows, n_cols_b, a, 0, workspace, workspace_bytes, stream);
 }
 
 extern "C" int gcg_spgemm_fill_csr_f32(int64_t n_rows, int64_t n_cols_b, const int32_t* a_indptr,

@@ -305,7 +305,7 @@ def spgemm(A: "CSRMatrix", B: "CSRMatrix", a_values=None) -> "CSRMatrix":
     wp = ws.data_ptr() + (-ws.data_ptr()) % 256
     row_nnz = torch.zeros(max(n, 1), dtype=torch.int32, device=dev)
     _lib.check(L.gcg_spgemm_count_csr(n, V, A.indptr.data_ptr(), A.indices.data_ptr(), B.indptr.data_ptr(),
-                                      B.indices.data_ptr(), row_nnz.data_ptr(), wp, wsb, stream),
+                                      B.indices.data_ptr(), 0, row_nnz.data_ptr(), wp, wsb, stream),
                "gcg_spgemm_count_csr")
     c_ip = torch.zeros(n + 1, dtype=torch.int64, device=dev)
     torch.cumsum(row_nnz[:n], 0, out=c_ip[1:])
@@ -319,6 +319,35 @@ def spgemm(A: "CSRMatrix", B: "CSRMatrix", a_values=None) -> "CSRMatrix":
                                          B.data.data_ptr(), c_ip.data_ptr(), c_ix.data_ptr(), c_d.data_ptr(), wp, wsb,
                                          stream), "gcg_spgemm_fill_csr_f32")
     return CSRMatrix(c_ip.to(torch.int32), c_ix, c_d, (n, V))
+
+
+def spgemm_pattern(A: "CSRMatrix", B: "CSRMatrix", drop_diagonal=False) -> "CSRMatrix":
+    """Sorted column pattern of A * B (values ignored; the result's data are ones), optionally without the
+    diagonal -- gcg_spgemm_count_csr / gcg_spgemm_fill_pattern_csr (graph projection, data.py:226-250)."""
+    if A.shape[1] != B.shape[0]:
+        raise ValueError("spgemm_pattern: A is %s but B is %s" % (A.shape, B.shape))
+    dev = A.device
+    L = _lib.lib()
+    n, V = A.shape[0], B.shape[1]
+    stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    wsb = int(L.gcg_spgemm_workspace_bytes(V))
+    ws = torch.empty(wsb + 256, dtype=torch.uint8, device=dev)
+    wp = ws.data_ptr() + (-ws.data_ptr()) % 256
+    row_nnz = torch.zeros(max(n, 1), dtype=torch.int32, device=dev)
+    dd = int(bool(drop_diagonal))
+    _lib.check(L.gcg_spgemm_count_csr(n, V, A.indptr.data_ptr(), A.indices.data_ptr(), B.indptr.data_ptr(),
+                                      B.indices.data_ptr(), dd, row_nnz.data_ptr(), wp, wsb, stream),
+               "gcg_spgemm_count_csr")
+    c_ip = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+    torch.cumsum(row_nnz[:n], 0, out=c_ip[1:])
+    nnz = int(c_ip[-1].item())
+    if nnz >= 2 ** 31 - 1:
+        raise _lib.GcgError("spgemm_pattern: the product has %d non-zeros (int32 CSR offsets)" % nnz)
+    c_ix = torch.empty(nnz, dtype=torch.int32, device=dev)
+    _lib.check(L.gcg_spgemm_fill_pattern_csr(n, V, A.indptr.data_ptr(), A.indices.data_ptr(), B.indptr.data_ptr(),
+                                             B.indices.data_ptr(), dd, c_ip.data_ptr(), c_ix.data_ptr(), wp, wsb,
+                                             stream), "gcg_spgemm_fill_pattern_csr")
+    return CSRMatrix(c_ip.to(torch.int32), c_ix, torch.ones(nnz, dtype=torch.float32, device=dev), (n, V))
 
 
 def smooth_features(H, X, device="cuda") -> "CSRMatrix":

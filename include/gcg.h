@@ -344,19 +344,29 @@ int gcg_csr_permute_host(int64_t n_rows, const int32_t* h_indptr, const int32_t*
  * bit-identical to scipy.  Differences: entries whose sum is exactly 0.0 are kept (scipy's csr_matmat
  * drops them); B must not hold duplicate column entries inside a row.
  *
- * Protocol: (1) gcg_spgemm_count_csr -> row_nnz[n_rows]; (2) caller builds c_indptr
+ * Protocol: (1) gcg_spgemm_count_csr (drop_diagonal = 0) -> row_nnz[n_rows]; (2) caller builds c_indptr
  * (int64[n_rows+1], exclusive scan) and allocates c_indices / c_vals; (3) gcg_spgemm_fill_csr_f32.
  * a_vals is float64 when a_is_f64 != 0 (float64 sums, the reference's case), else float32 (float32
  * sums, scipy's promotion rule for float32 * float32).
  * Workspace: gcg_spgemm_workspace_bytes(n_cols_b); zero-initialised by the calls themselves. */
 int64_t gcg_spgemm_workspace_bytes(int64_t n_cols_b);
 int gcg_spgemm_count_csr(int64_t n_rows, int64_t n_cols_b, const int32_t* a_indptr, const int32_t* a_indices,
-                         const int32_t* b_indptr, const int32_t* b_indices, int32_t* row_nnz,
+                         const int32_t* b_indptr, const int32_t* b_indices, int drop_diagonal, int32_t* row_nnz,
                          void* workspace, int64_t workspace_bytes, void* stream);
 int gcg_spgemm_fill_csr_f32(int64_t n_rows, int64_t n_cols_b, const int32_t* a_indptr, const int32_t* a_indices,
                             const void* a_vals, int a_is_f64, const int32_t* b_indptr, const int32_t* b_indices,
                             const float* b_vals, const int64_t* c_indptr, int32_t* c_indices, float* c_vals,
                             void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Pattern-only product (no values): the sorted column pattern of A * B, optionally without the diagonal.
+ * With A = R^T, B = R (R[m, t] = 1 when target user t is a neighbour of node m in the @-mention graph,
+ * self loops included) this is the user-user graph of efficient_collaboration_weighted_projected_graph2
+ * (data.py:226-250): every node's target neighbours become a clique.  Count with gcg_spgemm_count_csr
+ * (same drop_diagonal), then fill. */
+int gcg_spgemm_fill_pattern_csr(int64_t n_rows, int64_t n_cols_b, const int32_t* a_indptr, const int32_t* a_indices,
+                                const int32_t* b_indptr, const int32_t* b_indices, int drop_diagonal,
+                                const int64_t* c_indptr, int32_t* c_indices, void* workspace,
+                                int64_t workspace_bytes, void* stream);
 
 /* Device-side minibatch slicing, `inputs[excerpt]` of iterate_minibatches (mlp.py:81-91):
  * out CSR = rows d_rows[0..n_sel) of the input CSR, entry order inside a row preserved.
