@@ -144,6 +144,24 @@ def cpu_mlp_epoch(Xc_host, y_train, hidden, n_classes, batch, n_batches, sample_
     return per_batch * n_batches * 1e3, sample_batches
 
 
+def cpu_projection(B, n_targets, budget_pairs=4e6):
+    """cpu_baseline of the mention-graph projection (used by scripts/projection_bench.py):
+    the plain-Python port of data.py:226-250 on the first nodes whose clique pairs fit ``budget_pairs``,
+    scaled to the whole graph by pair count.  Returns (ms for the whole graph, nodes sampled)."""
+    from oracle import graph_oracle as gro
+    import scipy.sparse as sp
+    B = sp.csr_matrix(B)
+    tdeg = np.diff(sp.csr_matrix(B[:, :n_targets]).indptr).astype(np.float64)
+    pairs = tdeg * tdeg
+    cum = np.cumsum(pairs)
+    k = int(min(len(cum), max(1, np.searchsorted(cum, budget_pairs) + 1)))
+    adj = gro.adjacency_sets(B[:k])
+    t0 = time.perf_counter()
+    gro.project(adj, n_targets)
+    dt = time.perf_counter() - t0
+    return dt * cum[-1] / max(cum[k - 1], 1.0) * 1e3, k
+
+
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path (oracle port; Theano is not
     installable here) on the box's host cores, bounded sample, same metric/unit/config."""

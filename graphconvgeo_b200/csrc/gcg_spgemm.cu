@@ -8,8 +8,9 @@
 // touched by the current row.  A's entries are visited strictly in stored order and the 32 lanes split
 // one row of B, so every output entry receives its additions `sums[k] += a*b` (from 0, multiply and add
 // rounded separately) in exactly scipy's csr_matmat order -> bit-identical values after the single
-// float32 rounding.  The row is then emitted by one sweep over the touched range of the bitmap, which
-// yields ascending columns (the canonical form `X_conv.tocsr().astype('float32')` ends up in, because
+// float32 rounding.  The row is then emitted by one sweep over the non-empty 1024-column groups of the
+// bitmap (a second-level summary bitmap names them, so short rows over a wide column space -- the graph
+// projection -- do not pay for the range they span), which yields ascending columns (the canonical form `X_conv.tocsr().astype('float32')` ends up in, because
 // scipy's astype sorts the indices) and resets accumulator and bitmap for the next row.
 #include <cub/device/device_radix_sort.cuh>
 
@@ -25,20 +26,23 @@ constexpr int64_t kSpgemmBudget = 4LL << 30;  // bytes of dense accumulators acr
 
 struct SpgemmLayout {
   int workers;
-  int64_t vpad;              // columns padded to a multiple of 1024 (32 bitmap words)
-  int64_t bitmap_off, acc_off, total;
+  int64_t vpad;              // columns padded to a multiple of 1024 (32 bitmap words = one group)
+  int64_t sum_words;         // summary words per worker (one bit per group), a multiple of 32
+  int64_t bitmap_off, summary_off, acc_off, total;
 };
 
 SpgemmLayout spgemm_layout(int64_t n_cols) {
   SpgemmLayout L;
   L.vpad = (n_cols + 1023) / 1024 * 1024;
   if (L.vpad == 0) L.vpad = 1024;
-  int64_t w = kSpgemmBudget / (L.vpad * 8 + L.vpad / 8);
+  L.sum_words = ((L.vpad >> 10) + 1023) / 1024 * 32;
+  int64_t w = kSpgemmBudget / (L.vpad * 8 + L.vpad / 8 + L.sum_words * 4);
   w = std::min<int64_t>(w, (int64_t)kNumSMs * 16);
   w = std::max<int64_t>(w, (int64_t)kNumSMs);
   L.workers = (int)(w / kWarpsPerCta * kWarpsPerCta);
   L.bitmap_off = 256;
-  L.acc_off = L.bitmap_off + (int64_t)L.workers * (L.vpad / 8);
+  L.summary_off = L.bitmap_off + (int64_t)L.workers * (L.vpad / 8);
+  L.acc_off = L.summary_off + (int64_t)L.workers * L.sum_words * 4;
   L.total = L.acc_off + (int64_t)L.workers * L.vpad * 8;
   return L;
 }
@@ -56,8 +60,10 @@ struct SpgemmArgs {
   float* c_vals;
   int32_t* counter;
   uint32_t* bitmap;
+  uint32_t* summary;
   double* acc;
   int64_t vpad;
+  int64_t sum_words;
   int n_rows;
   int drop_diagonal;   // skip column == row (graph projection: no self edges)
   int pattern_only;    // NUMERIC pass without values (c_vals == NULL)
@@ -87,6 +93,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) spgemm_rows_kernel(SpgemmAr
   const int lane = threadIdx.x & 31;
   const int worker = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
   uint32_t* bitmap = a.bitmap + (size_t)worker * (a.vpad >> 5);
+  uint32_t* summary = a.summary + (size_t)worker * a.sum_words;     // bit g: group g (1024 columns) is non-empty
   AT* acc = reinterpret_cast<AT*>(a.acc + (size_t)worker * a.vpad);
   const AT* a_vals = reinterpret_cast<const AT*>(a.a_vals);
 
@@ -104,11 +111,16 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) spgemm_rows_kernel(SpgemmAr
       const int qb = a.b_indptr[j], qe = a.b_indptr[j + 1];
       for (int q0 = qb; q0 < qe; q0 += 32) {
         const int q = q0 + lane;
-        if (q < qe) {
-          const int k = a.b_indices[q];
+        const int k = (q < qe) ? a.b_indices[q] : -1;
+        // group marks: lanes whose left neighbour is in the same 1024-column group skip theirs (B's rows are
+        // normally sorted, so a chunk issues a handful); both atomics are fire-and-forget reductions
+        const int g = k >> 10;
+        const int g_left = __shfl_up_sync(0xffffffffu, g, 1);
+        if (k >= 0) {
           kmin = min(kmin, k);
           kmax = max(kmax, k);
           atomicOr(&bitmap[k >> 5], 1u << (k & 31));
+          if (lane == 0 || g != g_left) atomicOr(&summary[g >> 5], 1u << (g & 31));
           if (NUMERIC && !a.pattern_only) acc[k] = add_rn(acc[k], mul_rn(av, (AT)a.b_vals[q]));   // sums[k] += v * Bx[kk]
         }
         __syncwarp();   // the next chunk may touch the same columns from other lanes
@@ -127,34 +139,49 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) spgemm_rows_kernel(SpgemmAr
       out_val = a.c_vals + base;
     }
     if (kmax >= 0) {
-      const int w_end = kmax >> 5;
-      for (int w0 = kmin >> 5; w0 <= w_end; w0 += 32) {
-        const int w = w0 + lane;
-        uint32_t bits = (w <= w_end) ? __ldcg(&bitmap[w]) : 0u;   // set by atomics at L2: do not trust L1
-        if (bits) bitmap[w] = 0u;
-        if (a.drop_diagonal && w == (row >> 5)) bits &= ~(1u << (row & 31));
-        const int c = __popc(bits);
-        int incl = c;
+      // two-level sweep: summary words -> non-empty groups -> the group's 32 bitmap words (one per lane)
+      const int s_end = kmax >> 15;
+      for (int s0 = kmin >> 15; s0 <= s_end; s0 += 32) {
+        const int sw = s0 + lane;
+        const uint32_t sbits = (sw <= s_end) ? __ldcg(&summary[sw]) : 0u;   // set by atomics at L2: bypass L1
+        if (sbits) summary[sw] = 0u;
+        unsigned lanes = __ballot_sync(0xffffffffu, sbits != 0u);
+        while (lanes) {
+          const int src = __ffs(lanes) - 1;
+          lanes &= lanes - 1;
+          uint32_t groups = __shfl_sync(0xffffffffu, sbits, src);
+          const int gbase = (s0 + src) << 5;
+          while (groups) {
+            const int g = gbase + __ffs(groups) - 1;
+            groups &= groups - 1;
+            const int w = (g << 5) + lane;
+            uint32_t bits = __ldcg(&bitmap[w]);
+            if (bits) bitmap[w] = 0u;
+            if (a.drop_diagonal && w == (row >> 5)) bits &= ~(1u << (row & 31));
+            const int c = __popc(bits);
+            int incl = c;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const int t = __shfl_up_sync(0xffffffffu, incl, o);
-          if (lane >= o) incl += t;
-        }
-        if (NUMERIC && bits) {
-          int pos = cnt + incl - c;
-          while (bits) {
-            const int bpos = __ffs(bits) - 1;
-            bits &= bits - 1;
-            const int k = (w << 5) + bpos;
-            out_idx[pos] = k;
-            if (!a.pattern_only) {
-              out_val[pos] = (float)acc[k];
-              acc[k] = AT(0);
+            for (int o = 1; o < 32; o <<= 1) {
+              const int t = __shfl_up_sync(0xffffffffu, incl, o);
+              if (lane >= o) incl += t;
             }
-            ++pos;
+            if (NUMERIC && bits) {
+              int pos = cnt + incl - c;
+              while (bits) {
+                const int bpos = __ffs(bits) - 1;
+                bits &= bits - 1;
+                const int k = (w << 5) + bpos;
+                out_idx[pos] = k;
+                if (!a.pattern_only) {
+                  out_val[pos] = (float)acc[k];
+                  acc[k] = AT(0);
+                }
+                ++pos;
+              }
+            }
+            cnt += __shfl_sync(0xffffffffu, incl, 31);
           }
         }
-        cnt += __shfl_sync(0xffffffffu, incl, 31);
       }
     }
     if (!NUMERIC && lane == 0) a.row_nnz[row] = cnt;
@@ -250,6 +277,8 @@ static int spgemm_common(bool numeric, int64_t n_rows, int64_t n_cols_b, SpgemmA
   char* ws = reinterpret_cast<char*>(workspace);
   a.counter = reinterpret_cast<int32_t*>(ws);
   a.bitmap = reinterpret_cast<uint32_t*>(ws + L.bitmap_off);
+  a.summary = reinterpret_cast<uint32_t*>(ws + L.summary_off);
+  a.sum_words = L.sum_words;
   a.acc = reinterpret_cast<double*>(ws + L.acc_off);
   a.vpad = L.vpad;
   a.n_rows = (int)n_rows;

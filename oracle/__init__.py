@@ -19,6 +19,8 @@ Parity status (see DESIGN.md "Oracle"):
   executes the reference's own third-party routine; the CUDA SpGEMM is compared bit for bit.
   The minibatch MLP around it (``mlp_oracle.MLPOracle`` / ``fit``, mlp.py:121-314) is
   **unpinned** like the GCN and cross-checked against torch-CPU autograd.
+* Mention-graph projection (``graph_oracle.py``, data.py:226-250,364-370): **pinned** -- equal to
+  golden graphs produced by the reference's own function (tests/golden/make_projection_golden.py).
 * kd-tree labels (``kdtree_oracle.py``): **pinned** -- checked bit-for-bit
   against the reference's own ``kdtree.py`` (imported from /root/reference by
   ``tests/golden/make_kdtree_golden.py``, outputs committed under
