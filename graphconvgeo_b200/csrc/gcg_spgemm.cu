@@ -10,8 +10,9 @@
 // rounded separately) in exactly scipy's csr_matmat order -> bit-identical values after the single
 // float32 rounding.  The row is then emitted by one sweep over the non-empty 1024-column groups of the
 // bitmap (a second-level summary bitmap names them, so short rows over a wide column space -- the graph
-// projection -- do not pay for the range they span), which yields ascending columns (the canonical form `X_conv.tocsr().astype('float32')` ends up in, because
-// scipy's astype sorts the indices) and resets accumulator and bitmap for the next row.
+// projection -- do not pay for the range they span), which yields ascending columns (the canonical form
+// `X_conv.tocsr().astype('float32')` ends up in, because scipy's astype sorts the indices) and resets
+// accumulator and bitmap for the next row.
 #include <cub/device/device_radix_sort.cuh>
 
 #include <algorithm>
@@ -22,7 +23,8 @@ namespace gcg {
 namespace {
 
 constexpr int kWarpsPerCta = 4;
-constexpr int64_t kSpgemmBudget = 4LL << 30;  // bytes of dense accumulators across all workers
+constexpr int64_t kSpgemmBudget = 12LL << 30;  // bytes of dense accumulators across all workers (HBM is 180 GB)
+constexpr int kMaxWarpsPerSM = 32;             // latency-bound kernel: ncu showed 22 % occupancy at 14 warps/SM
 
 struct SpgemmLayout {
   int workers;
@@ -37,7 +39,7 @@ SpgemmLayout spgemm_layout(int64_t n_cols) {
   if (L.vpad == 0) L.vpad = 1024;
   L.sum_words = ((L.vpad >> 10) + 1023) / 1024 * 32;
   int64_t w = kSpgemmBudget / (L.vpad * 8 + L.vpad / 8 + L.sum_words * 4);
-  w = std::min<int64_t>(w, (int64_t)kNumSMs * 16);
+  w = std::min<int64_t>(w, (int64_t)kNumSMs * kMaxWarpsPerSM);
   w = std::max<int64_t>(w, (int64_t)kNumSMs);
   L.workers = (int)(w / kWarpsPerCta * kWarpsPerCta);
   L.bitmap_off = 256;
