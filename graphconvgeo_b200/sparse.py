@@ -165,6 +165,8 @@ class CSRMatrix:
         """A[rows, :] built on the GPU (gcg_csr_gather_rows_device) -- `inputs[excerpt]` of
         iterate_minibatches (mlp.py:81-91).  ``rows``: host int array; entry order inside rows is kept."""
         rows = np.ascontiguousarray(np.asarray(rows), dtype=np.int32)
+        if len(rows) and (rows.min() < 0 or rows.max() >= self.shape[0]):
+            raise IndexError("row index out of range for a matrix with %d rows" % self.shape[0])
         if self.host is None:
             self.host = (self.indptr.cpu().numpy(), None, None)
         ip = self.host[0]
