@@ -15,7 +15,12 @@ def declared_symbols():
 def test_header_declares_the_hot_path():
     syms = declared_symbols()
     for must in ["gcg_spmm_csr_f32", "gcg_gemm_f32", "gcg_softmax_ce_f32", "gcg_adam_step_f32",
-                 "gcg_highway_bwd_f32", "gcg_kdtree_fit_host", "gcg_plan_create_csr", "gcg_last_error"]:
+                 "gcg_highway_bwd_f32", "gcg_kdtree_fit_host", "gcg_plan_create_csr", "gcg_last_error",
+                 # widened rows: A_hat on the device, smoothing SpGEMM, minibatch slicing,
+                 # graph projection, label pipeline
+                 "gcg_ahat_fill_device", "gcg_spgemm_count_csr", "gcg_spgemm_fill_csr_f32",
+                 "gcg_spgemm_fill_pattern_csr", "gcg_csr_gather_rows_device", "gcg_csr_transpose_device",
+                 "gcg_haversine_nearest_f64"]:
         assert must in syms
 
 
@@ -46,6 +51,12 @@ def test_error_convention(built_lib):
         assert "GCG_ERR_BAD_ARG" in str(e)
     else:
         raise AssertionError("check() must raise")
+    # argument checks of the widened rows fire before any CUDA call as well
+    assert L.gcg_spgemm_count_csr(4, 4, None, None, None, None, 0, None, None, 0, None) == -1
+    assert L.gcg_spgemm_fill_csr_f32(4, 4, None, None, None, 1, None, None, None, None, None, None, None, 0, None) == -1
+    assert b"c_indptr is NULL" in L.gcg_last_error()
+    assert L.gcg_csr_transpose_device(-1, 4, 0, None, None, None, None, None, None, None, 0, None) == -1
+    assert L.gcg_spgemm_workspace_bytes(9000) > 9000 * 8 * 148
 
 
 def test_no_cpu_fallback_in_product_path():
