@@ -74,6 +74,26 @@ def main():
             remote = n_rows * fp * 4 * (1.0 if mode == "one_peer" else (world - 1) / world)
             results.append(dict(run_bytes=fp * 4, mode=mode, ms=float(t.item()),
                                 remote_GBps=remote / (float(t.item()) * 1e-3) / 1e9))
+    # the forward transpose of the epoch: gcg_push_cols_f32 on a [n_loc, 600] operand, every rank to every peer
+    F = 600
+    fp = (-(-F // world) + 3) // 4 * 4
+    n_loc = total_floats // (world * fp)
+    z = torch.randn(n_loc, F, dtype=torch.float32, device=dev)
+    times = []
+    for it in range(6):
+        dist.all_reduce(flag)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _lib.check(L.gcg_push_cols_f32(z.data_ptr(), F, n_loc, F, world, fp, peer_arr, rank * n_loc, stream), "push_cols")
+        e1.record()
+        torch.cuda.synchronize()
+        if it:
+            times.append(e0.elapsed_time(e1))
+    t = torch.tensor([min(times)], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    remote = n_loc * fp * 4 * (world - 1)
+    results.append(dict(kernel="push_cols", n_loc=n_loc, F=F, Fp=fp, ms=float(t.item()),
+                        remote_GBps=remote / (float(t.item()) * 1e-3) / 1e9))
     if rank == 0:
         print(json.dumps(dict(world=world, bytes_per_push=total_floats * 4, results=results)))
     dist.barrier()
