@@ -93,36 +93,144 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------ CPU baseline
-def cpu_reference_epoch(workload, n_layers, highway, scale, epochs=1, threads=None, warmup=0):
-    """The reference's CPU path (oracle port: scipy csr@dense + BLAS, float32) on a bounded sample
-    of the workload: the same shape generator at `scale` of the node/vocabulary counts.  Returns
-    (mean ms per epoch on the sample over `epochs` timed epochs, description, threads)."""
+def host_workload(workload, log_fn=log):
+    """The bench's own workload (same seeds, same N / V / nnz / regions as the GPU arm) as host arrays, built
+    WITHOUT libgcg.so: raw adjacency / TF-IDF / coordinates from the seeded torch generators (on the GPU when
+    there is one -- data plumbing -- else on the CPU), then A_hat by the oracle's restatement of
+    tensormain.py:170-180,221 and the labels by the oracle's kd-tree / nearest-median (kdtree.py, data.py:399-421)."""
+    import scipy.sparse as sp
+    import torch
     from graphconvgeo_b200 import synth
     from oracle import gcn_oracle as go
-    threads = threads or os.cpu_count()
-    w = synth.make_workload(workload, scale=scale)
+    from oracle import kdtree_oracle as ko
+    t0 = time.time()
+    dev = "cuda" if torch.cuda.is_available() else "cpu"
+    cfg, n, locs, (ip, ix), (xip, xix, xv) = synth.make_raw_device(workload, device=dev, seed=77)
+    adj = sp.csr_matrix((np.ones(ix.numel(), np.float64), ix.cpu().numpy(), ip.cpu().numpy()), shape=(n, n))
+    X = sp.csr_matrix((xv.cpu().numpy(), xix.cpu().numpy(), xip.cpu().numpy()), shape=(n, cfg["vocab"]))
+    del ip, ix, xip, xix, xv
+    if dev == "cuda":
+        torch.cuda.empty_cache()
+    t1 = time.time()
+    A = go.build_ahat(adj)
+    del adj
+    t2 = time.time()
+    n_train = cfg["n_train"]
+    y_train, n_leaves = ko.kdtree_labels(locs[:n_train], cfg["bucket"])
+    med = ko.cluster_medians(locs[:n_train], y_train)
+    y_other = ko.nearest_median_labels(locs[n_train:], med)
+    Y = np.concatenate([y_train, y_other]).astype(np.int64)
+    t3 = time.time()
+    log_fn("[reference] workload %s on the host: raw %.1fs (torch on %s), A_hat (oracle) %.1fs, labels (oracle) %.1fs"
+           % (workload, t1 - t0, dev, t2 - t1, t3 - t2))
+    meta = dict(n=n, vocab=cfg["vocab"], hidden=cfg["hidden"], regions=int(Y.max()) + 1, nnz_A=int(A.nnz),
+                nnz_X=int(X.nnz), max_degree=int(np.diff(A.indptr).max()))
+    return X, A, Y, np.arange(n_train, dtype=np.int32), meta
+
+
+# timed epochs the reference arm runs per workload: one Twitter-World epoch of the oracle takes ~100 s of host time
+REF_EPOCH_CAP = {"twitter-world": (1, 1), "twitter-us": (1, 3), "geotext": (3, 20), "tiny": (3, 20)}    # (warm-up, timed)
+
+
+def cpu_reference_epochs(workload, n_layers, highway, steps, warmup):
+    """The reference's CPU path -- the oracle port (scipy csr@dense on 1 thread, what Theano's S.dot dispatches
+    to, + multi-threaded BLAS) -- on the FULL workload: whole epochs of mlpconv.py:293-295, timed one by one."""
+    from oracle import gcn_oracle as go
+    threads = os.cpu_count()
+    X, A, Y, train_idx, meta = host_workload(workload)
+    # a whole epoch keeps ~16 [N, max(h, C)] float32 arrays alive at its peak; refuse rather than swap / be OOM-killed
+    need = 16.0 * meta["n"] * max(meta["hidden"], meta["regions"]) * 4 + 40.0 * meta["vocab"] * meta["hidden"]
+    try:
+        import psutil
+        avail = float(psutil.virtual_memory().available)
+    except Exception:
+        avail = float("inf")
+    if need > 0.9 * avail and os.environ.get("GCG_REF_FORCE") != "1":
+        print(json.dumps({"impl": "reference", "unavailable": "host memory: the %s oracle epoch needs ~%.0f GB, "
+                          "%.0f GB available" % (workload, need / 1e9, avail / 1e9)}), flush=True)
+        raise SystemExit(0)
     rng = np.random.RandomState(0)
-    params = go.init_params(rng, w.X.shape[1], w.hidden, w.n_classes, n_layers, highway)
-    net = go.GCNOracle(w.X, w.A_hat, n_layers, highway, (1e-6, 1e-6))
-    y = w.Y[w.train_indices].astype(np.int32)
+    params = go.init_params(rng, X.shape[1], meta["hidden"], meta["regions"], n_layers, highway)
+    net = go.GCNOracle(X, A, n_layers, highway, (1e-6, 1e-6))
+    y = Y[train_idx].astype(np.int32)
     st = go.AdamState(params)
-    times = []
-    for i in range(warmup + epochs):
+    cap_w, cap_s = REF_EPOCH_CAP[workload]
+    warmup, steps = min(warmup, cap_w), max(1, min(steps, cap_s))
+    times, loss = [], None
+    for i in range(warmup + steps):
         t0 = time.perf_counter()
-        loss, acc, grads, _c = net.loss_and_grads(params, w.train_indices, y)
+        loss, acc, grads, _c = net.loss_and_grads(params, train_idx, y, lean=True)
         go.adam_step(params, grads, st)
         dt = (time.perf_counter() - t0) * 1e3
+        del grads, _c
+        import resource
+        log("[reference] epoch %d: %.1f ms  loss %.5f acc %.4f  (peak RSS %.1f GB)"
+            % (i, dt, float(loss), acc, resource.getrusage(resource.RUSAGE_SELF).ru_maxrss / 1e6))
         if i >= warmup:
             times.append(dt)
-        if sum(times) > 120e3:
-            break
-    desc = ("%d epoch(s) of the oracle port (scipy csr@dense, 1 thread as under Theano, + BLAS on %d threads) on the %s "
-            "generator at scale %.4g: %d nodes, vocab %d, nnzA %d, nnzX %d; value = sample ms / scale"
-            % (len(times), threads, workload, scale, w.meta["n"], w.X.shape[1], w.meta["nnz_A"], w.meta["nnz_X"]))
-    return float(np.mean(times)), desc, threads, len(times)
+    desc = ("%d whole epoch(s) (after %d warm-up) of the oracle port (scipy csr@dense on 1 thread, as under Theano, + BLAS on "
+            "%d threads) on the full %s workload: %d nodes, vocab %d, %d regions, nnzA %d, nnzX %d"
+            % (len(times), warmup, threads, workload, meta["n"], meta["vocab"], meta["regions"], meta["nnz_A"], meta["nnz_X"]))
+    return float(np.mean(times)), desc, threads, len(times), warmup, meta
 
 
-CPU_SCALE = {"twitter-world": 1.0 / 64, "twitter-us": 1.0 / 24, "geotext": 1.0, "tiny": 1.0}
+def cpu_baseline_sample(m, wl, n_layers, highway, row_fraction=1.0 / 32, seed=5):
+    """cpu_baseline of the GPU arm: a BOUNDED sample of the same full-size workload.  The epoch's row-parallel
+    products (X.W1, A_hat.H, the dense projections and their gradients) are timed with the oracle's own routines
+    (scipy csr@dense, BLAS) on a random ``row_fraction`` of the output rows against FULL-size operands (all N
+    gathered rows, the whole vocabulary, all regions) and scaled by 1/row_fraction; Adam is timed on the full
+    parameter set.  Same N, V, C and non-zeros as the GPU arm; `--impl reference` runs whole epochs."""
+    import scipy.sparse as sp
+    from oracle import gcn_oracle as go
+    t_start = time.perf_counter()
+    X = m.Xd.to_scipy()                       # the GPU arm's own (region-reordered) inputs, copied to the host
+    A = m.l_hid1.H.to_scipy()
+    N, V = X.shape
+    h, C = wl.hidden, wl.n_classes
+    rng = np.random.RandomState(seed)
+    rows = np.sort(rng.choice(N, size=max(1, int(N * row_fraction)), replace=False))
+    Xr, Ar = X[rows], A[rows]
+    XrT = sp.csr_matrix(Xr.T)
+    params = go.init_params(np.random.RandomState(0), V, h, C, n_layers, highway)
+    W1, Wout = params[0], params[-2]
+    Hfull = rng.standard_normal((N, h)).astype(np.float32)
+    Hr = np.ascontiguousarray(Hfull[rows])
+    Gr = rng.standard_normal((len(rows), C)).astype(np.float32)
+    t = {}
+
+    def timed(key, fn, reps=1):
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            r = fn()
+        t[key] = (time.perf_counter() - t0) / reps
+        return r
+    timed("X.W1", lambda: Xr @ W1)
+    timed("A_hat.H (F=h)", lambda: Ar @ Hfull)
+    timed("X^T.dZ1", lambda: XrT @ Hr)
+    timed("H.W (h x h)", lambda: np.dot(Hr, params[2] if n_layers > 2 else W1[:h, :h].copy()))
+    timed("H^T.dZ (h x h)", lambda: np.dot(Hr.T, Hr))
+    timed("H.W_out", lambda: np.dot(Hr, Wout))
+    timed("H^T.dP_out", lambda: np.dot(Hr.T, Gr))
+    timed("dP_out.W_out^T", lambda: np.dot(Gr, Wout.T))
+    grads = [np.zeros_like(p) for p in params]
+    st = go.AdamState(params)
+    timed("adam (all parameters)", lambda: go.adam_step(params, grads, st))
+    n_hid = n_layers - 2
+    gemm_hh = (2 if highway else 1) * n_hid       # H.W (+ H.Wg) forward; twice that many of each kind backward
+    scaled = (t["X.W1"] + t["X^T.dZ1"]
+              + (2 + 2 * n_hid) * t["A_hat.H (F=h)"]                      # fwd + bwd per hidden conv layer, layer 1 included
+              + 2 * t["A_hat.H (F=h)"] * (n_train_rows(m) / float(N))     # output layer propagates the target rows only
+              + gemm_hh * (t["H.W (h x h)"] + t["H^T.dZ (h x h)"] + t["H.W (h x h)"])
+              + t["H.W_out"] + t["H^T.dP_out"] + t["dP_out.W_out^T"]) / row_fraction + t["adam (all parameters)"]
+    desc = ("oracle routines (scipy csr@dense 1 thread + BLAS on %d threads) on a random %.4g of the output rows of the "
+            "full %s workload (%d nodes, vocab %d, %d regions, nnzA %d, nnzX %d; operands full size), scaled by %g; "
+            "Adam on all parameters; %.1f s of host time" % (os.cpu_count(), row_fraction, wl.name, N, V, C, A.nnz, X.nnz,
+                                                             1.0 / row_fraction, time.perf_counter() - t_start))
+    return scaled * 1e3, desc, {k: round(v * 1e3, 2) for k, v in t.items()}
+
+
+def n_train_rows(m):
+    return m.ti_train.n
 
 
 def cpu_mlp_epoch(Xc_host, y_train, hidden, n_classes, batch, n_batches, sample_batches=4):
@@ -164,19 +272,20 @@ def cpu_projection(B, n_targets, budget_pairs=4e6):
 
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path (oracle port; Theano is not
-    installable here) on the box's host cores, bounded sample, same metric/unit/config."""
+    installable here) on the box's host cores, on the SAME workload as the GPU arm (same seeds, N, V, regions,
+    non-zeros), whole epochs; `steps` / `warmup` report what was actually timed (a Twitter-World epoch takes
+    ~100 s of host time, so at most 1 + 1 are run).  Nothing of libgcg.so is loaded on this path."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    scale = CPU_SCALE[args.workload]
-    ms_sample, desc, threads, n_timed = cpu_reference_epoch(args.workload, args.layers, bool(args.highway), scale,
-                                                            epochs=args.steps, warmup=min(args.warmup, 1))
-    ms = ms_sample / scale
+    ms, desc, threads, n_timed, n_warm, meta = cpu_reference_epochs(args.workload, args.layers, bool(args.highway),
+                                                                     args.steps, args.warmup)
     line = {
         "impl": "reference", "metric": "gcn_fwd_bwd_epoch_ms", "value": ms, "unit": "ms", "n_gpus": args.gpus,
-        "steps": n_timed, "warmup": min(args.warmup, 1), "ms_per_step": ms, "higher_is_better": False,
+        "steps": n_timed, "warmup": n_warm, "ms_per_step": ms, "higher_is_better": False,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": bench_config(args),
+        "config": dict(bench_config(args), nodes=meta["n"], vocab=meta["vocab"], hidden=meta["hidden"],
+                       regions=meta["regions"], nnz_A=meta["nnz_A"], nnz_X=meta["nnz_X"], max_degree=meta["max_degree"]),
         "cpu_baseline": {"value": ms, "unit": "ms", "cores": threads, "kind": "port", "sample": desc},
         "e2e": {"value": ms, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -223,6 +332,7 @@ def run_gpu(args):
     if world > 1:
         from graphconvgeo_b200.dist import DistMLPCONV
         m = DistMLPCONV(partition=args.partition, peer_memory=not args.no_peer_memory, **model_kwargs)
+        m.keep_host_inputs = not args.no_parity
     else:
         m = MLPCONV(**model_kwargs)
     t0 = time.time()
@@ -300,6 +410,9 @@ def run_gpu(args):
     # ---------------- roofline of the headline kernel: A_hat . H  (F = hidden)
     roof = spmm_roofline(m, wl, dev)          # collective in row-partitioned mode: every rank calls it
 
+    # ---------------- parity of one training step at this size, operation by operation on sampled rows
+    parity = None if args.no_parity else parity_block(m, args, rank)     # collective: every rank calls it
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -307,10 +420,10 @@ def run_gpu(args):
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        scale = CPU_SCALE[args.workload]
-        ms, desc, threads, _n = cpu_reference_epoch(args.workload, args.layers, bool(args.highway), scale, epochs=1)
-        cpu = {"value": ms / scale, "unit": "ms", "cores": threads, "kind": "port", "sample": desc,
-               "sample_ms": ms}
+        frac = {"twitter-world": 1.0 / 32, "twitter-us": 1.0 / 16}.get(args.workload, 1.0)
+        ms, desc, per_op = cpu_baseline_sample(m, wl, args.layers, bool(args.highway), row_fraction=frac)
+        cpu = {"value": ms, "unit": "ms", "cores": os.cpu_count(), "kind": "port", "sample": desc,
+               "sample_op_ms": per_op}
 
     line = {
         "metric": "gcn_fwd_bwd_epoch_ms", "value": ms_per_step, "unit": "ms", "n_gpus": world, "steps": args.steps,
@@ -332,6 +445,16 @@ def run_gpu(args):
     if roof is not None:
         line["roofline"] = roof["roofline"]
         line["spmm"] = roof["detail"]
+    alg = algorithmic_table(m, wl, args.layers, bool(args.highway))
+    peak_gbs, _src = measured_peaks()
+    alg["floor_ms_at_measured_hbm_peak"] = alg["total_bytes"] / (peak_gbs * 1e9) * 1e3
+    line["algorithmic"] = alg
+    log("---- algorithmic work of one epoch (SURVEY 8d): %.2f GB compulsory, %.2f TFLOP; %.2f ms at %.0f GB/s ----"
+        % (alg["total_bytes"] / 1e9, alg["total_flops"] / 1e12, alg["floor_ms_at_measured_hbm_peak"], peak_gbs))
+    for r in alg["rows"]:
+        log("  %-46s x%-2d %9.3f GB %9.3f TFLOP" % (r["op"], r["count"], r["bytes_each"] / 1e9, r["flops_each"] / 1e12))
+    if parity is not None:
+        line["parity"] = parity
     if cpu is not None:
         line["cpu_baseline"] = cpu
     if breakdown is not None:
@@ -340,6 +463,63 @@ def run_gpu(args):
     os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
+
+
+def algorithmic_table(m, wl, n_layers, highway):
+    """compulsory traffic (each array touched once) and flops of one epoch, operation by operation.
+    B_spmm(nnz, n_out, n_in, F) = 8*nnz + 4*(n_out+1) + 4*n_in*F + 4*n_out*F."""
+    N, V, h, C = wl.meta["n"], wl.meta["vocab"], wl.hidden, wl.n_classes
+    nnzA, nnzX = wl.meta["nnz_A"], wl.meta["nnz_X"]
+    n_idx = len(wl.train_indices)
+    nnz_sub = int(round(nnzA * n_idx / float(N)))                  # A_hat[idx, :]
+    pf = bool(getattr(m.l_out, "propagate_first", False))
+    bs = lambda nnz, n_out, n_in, F: 8 * nnz + 4 * (n_out + 1) + 4 * n_in * F + 4 * n_out * F
+    gemm = lambda M, Nn, K: (4 * (M * K + K * Nn + M * Nn), 2 * M * Nn * K)
+    rows = [("X.W1 (a1)", 1, bs(nnzX, N, V, h), 2 * nnzX * h),
+            ("A_hat.Z, F=h, fwd (a4)", n_layers - 1, bs(nnzA, N, N, h), 2 * nnzA * h),
+            ("A_hat.dP, F=h, bwd (a5)", n_layers - 1 + (1 if pf else 0), bs(nnzA, N, N, h), 2 * nnzA * h),
+            ("X^T.dZ1 (a6)", 1, bs(nnzX, V, N, h), 2 * nnzX * h)]
+    n_hid = n_layers - 2
+    per_hid = (2 if highway else 1)
+    rows.append(("H.W / H.Wg, h x h, fwd (a3, a9)", n_hid * per_hid) + gemm(N, h, h))
+    rows.append(("H^T.dZ / H^T.dG, h x h (a7)", n_hid * per_hid) + gemm(h, h, N))
+    rows.append(("dZ.W^T / dG.Wg^T, h x h (a7)", n_hid * per_hid) + gemm(N, h, h))
+    if highway and n_hid:
+        rows.append(("highway mix epilogue + backward (a9)", n_hid, (16 + 28) * N * h, 12 * N * h))
+    if pf:
+        rows.append(("A_hat[idx,:].H, F=h (a3, propagate first)", 1, bs(nnz_sub, n_idx, N, h), 2 * nnz_sub * h))
+        rows.append(("(.).W_out, Q^T.dP, dP.W_out^T (a3, a7)", 3) + gemm(n_idx, C, h))
+    else:
+        rows.append(("H.W_out, H^T.dZ, dZ.W_out^T (a3, a7)", 3) + gemm(N, C, h))
+        rows.append(("A_hat[idx,:].Z, F=C (a3)", 1, bs(nnz_sub, n_idx, N, C), 2 * nnz_sub * C))
+        rows.append(("A_hat.dP, F=C, bwd (a5)", 1, bs(nnzA, N, N, C), 2 * nnzA * C))
+    rows.append(("softmax + CE + argmax + dLogits (a10)", 1, 8 * n_idx * C, 6 * n_idx * C))
+    n_par = sum(p.numel() for p in m.params)
+    rows.append(("Adam + elastic net (a11, a12)", 1, 28 * n_par, 12 * n_par))
+    tot_b = sum(c * b for _, c, b, _f in rows)
+    tot_f = sum(c * f for _, c, _b, f in rows)
+    return {"rows": [{"op": o, "count": c, "bytes_each": int(b), "flops_each": int(f)} for o, c, b, f in rows],
+            "total_bytes": int(tot_b), "total_flops": int(tot_f)}
+
+
+def parity_block(m, args, rank):
+    """One eager forward + one eager f_train of the benched model checked against the oracle on sampled rows
+    (oracle/sampled_parity.py): max over all operations of |gpu - oracle| / (1e-6 + 1e-4*|oracle|)."""
+    from oracle import sampled_parity
+    t0 = time.time()
+    g, m._graph = getattr(m, "_graph", None), None
+    try:
+        Xh, Ah = m.host_inputs()
+        rep = sampled_parity.check_training_step(m, Xh, Ah, n_rows=args.parity_rows, seed=3,
+                                                 log=log if rank == 0 else None)
+    finally:
+        m._graph = g
+    over = {k: round(v["max_scaled_err"], 3) for k, v in rep["checks"].items() if v["max_scaled_err"] > 1.0}
+    worst5 = sorted(rep["checks"].items(), key=lambda kv: -kv[1]["max_scaled_err"])[:5]
+    return {"max_scaled_err": rep["max_scaled_err"], "worst_check": rep["worst_check"], "n_checks": rep["n_checks"],
+            "tolerance": rep["tolerance"], "sampled_rows": args.parity_rows, "checks_over_tolerance": over,
+            "worst": {k: round(v["max_scaled_err"], 4) for k, v in worst5}, "seconds": round(time.time() - t0, 1),
+            "oracle": "scipy csr@dense + BLAS on the GPU path's own operands per operation; float64 for N-long sums"}
 
 
 def op_breakdown(m, dev):
@@ -485,6 +665,8 @@ def main():
     ap.add_argument("--highway", type=int, default=1)
     ap.add_argument("--random-graph", action="store_true", help="Chung-Lu graph without community structure")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the sampled-row oracle check of one training step")
+    ap.add_argument("--parity-rows", type=int, default=1024)
     ap.add_argument("--breakdown", action="store_true", help="per-op CUDA-event breakdown of one eager epoch")
     ap.add_argument("--no-peer-memory", action="store_true", help="feature mode: NCCL all-to-all instead of P2P stores")
     ap.add_argument("--partition", default="auto", choices=["auto", "feature", "row"],

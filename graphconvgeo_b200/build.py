@@ -20,7 +20,7 @@ INCLUDE = os.path.join(ROOT, "include")
 OBJ = os.path.join(HERE, "_obj")
 LIB = os.path.join(HERE, "libgcg.so")
 
-SOURCES = ["gcg_core.cu", "gcg_spmm.cu", "gcg_gemm.cu", "gcg_gemm_tc.cu", "gcg_elementwise.cu",
+SOURCES = ["gcg_core.cu", "gcg_spmm.cu", "gcg_spmm_stream.cu", "gcg_gemm.cu", "gcg_gemm_tc.cu", "gcg_elementwise.cu",
            "gcg_graph.cu", "gcg_host.cpp", "gcg_peer.cu", "gcg_spgemm.cu"]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -39,7 +39,7 @@ def _digest(paths):
     h = hashlib.sha256()
     for p in sorted(paths):
         with open(p, "rb") as f:
-            h.update(p.encode())
+            h.update(os.path.relpath(p, ROOT).encode())
             h.update(f.read())
     h.update(" ".join(NVCC_FLAGS).encode())
     return h.hexdigest()

@@ -237,7 +237,8 @@ __global__ void __launch_bounds__(256) softmax_ce_kernel(
   if (lane == 0) {
     if (pred) pred[i] = am;
     if (hit) hit[i] = (am == (int64_t)yi) ? 1.f : 0.f;
-    if (ce && yi >= 0 && yi < C) ce[i] = (m + logf(s)) - row[yi];
+    // a label outside [0, C) has no cross-entropy (the reference would raise an index error): NaN, never stale data
+    if (ce) ce[i] = (yi >= 0 && yi < C) ? (m + logf(s)) - row[yi] : __int_as_float(0x7fc00000);
   }
   if (probs || G) {
     for (int64_t c = lane; c < C; c += 32) {

@@ -1,0 +1,484 @@
+// Streaming CSR x dense SpMM (sm_100a): nnz-balanced spans, deep gather pipelines.
+//
+// Same contract as the register-gather kernel of gcg_spmm.cu (S.dot of lasagne_layers.py:26,65,67,84:
+// products summed in CSR order with separately rounded multiply and add -> bit-identical to scipy's
+// csr_matvecs), different execution shape:
+//
+//   * VIRTUAL ROWS.  The CSR rows, with every long row (> long_thresh non-zeros) cut into long_thresh-sized
+//     segments, form one ascending list of non-zero ranges vptr[0..n_v].  vdst[v] >= 0 names the output row,
+//     vdst[v] < 0 is ~segment: the partial goes to the workspace and spmm_finalize_kernel reduces the
+//     segments of a row in order (deterministic, no atomics) -- exactly the scheme of the other variants.
+//   * SPANS.  A span = a run of consecutive virtual rows holding about `span_nnz` non-zeros, restricted to a
+//     panel of float4 columns.  One warp executes one span: its non-zeros are ONE contiguous slice of the CSR
+//     arrays, streamed without draining the pipeline at row boundaries.  Every warp of a CTA carries the same
+//     amount of gather work, so no warp slot idles behind a hub row (the register-gather kernel's static 8
+//     rows per CTA lost 40 % of its warp time that way on the power-law mention graph).
+//   * SCHEDULE.  Spans are emitted block by block (gcg_plan_set_schedule): a block is a range of rows with a
+//     panel count.  Panel-major inside a block keeps `distinct columns of the block x panel bytes` resident
+//     in L2 while the block's rows gather from it (2-D tiling for communities larger than L2); interleaved
+//     order puts the panels of the same rows into the same CTA (thin per-warp state, whole-row DRAM locality).
+//   * TRANSPORT.  Gathered rows travel either through a per-warp shared-memory ring filled by cp.async
+//     (LDGSTS, 16 B per lane, no register cost: D-1 rows in flight per warp, ~150-200 KB per SM), or through
+//     a D-deep rotating register buffer (LDG.128).  Both are software pipelines over the span's non-zero
+//     stream: iteration t issues the gather of non-zero t and consumes non-zero t-(D-1).
+#include <algorithm>
+#include <limits.h>
+
+#include "gcg_spmm.cuh"
+
+namespace gcg {
+
+struct StreamSpan { int32_t v_beg, v_end, f4_beg, f4_cnt; };
+
+struct StreamSchedule {
+  int f4_total = 0, vplmax = 0, n_spans = 0;
+  StreamSpan* d_spans = nullptr;
+};
+
+struct StreamState {
+  std::mutex mu;
+  int64_t n_v = 0;
+  int32_t* d_vptr = nullptr;            // [n_v + 1]
+  int32_t* d_vdst = nullptr;            // [n_v]
+  std::vector<int32_t> h_vptr;          // host copies
+  std::vector<int32_t> h_row_v;         // [n_rows + 1] first virtual row of every row
+  std::vector<int32_t> blk_rows;        // [n_blocks + 1] row ranges of the schedule (empty = one block)
+  std::vector<int32_t> blk_panels;      // [n_blocks] >0: panel-major inside the block, <0: interleaved, |x| panels
+  std::map<int64_t, StreamSchedule> scheds;   // key: f4_total * 2^20 + span_nnz
+};
+
+static int g_stream_variant = 0;     // 0 = auto
+static int g_stream_span_nnz = 0;    // 0 = default
+
+void stream_state_destroy(StreamState* s) {
+  if (!s) return;
+  if (s->d_vptr) cudaFree(s->d_vptr);
+  if (s->d_vdst) cudaFree(s->d_vdst);
+  for (auto& kv : s->scheds)
+    if (kv.second.d_spans) cudaFree(kv.second.d_spans);
+  delete s;
+}
+
+// ------------------------------------------------------------------------------------------ device side
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint64_t pol) {
+  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
+// Epilogue of one float4 of a finished row, LEAN flavour: identity / +bias / relu, no gate, no accumulation --
+// every SpMM of an epoch except the gated layer's.  Code size matters here: the first version inlined the
+// general epilogue (tanhf / expf / gate mix) VPLMAX times per flush site and unrolled the loop D times; the
+// loop body outgrew the instruction cache and ncu showed the ring kernels stalled on instruction fetch
+// (stall_no_instruction 4-7 warps per issue) instead of on memory.  The kernel is therefore specialised on the
+// epilogue class at compile time (LEAN) and the ring loop body exists exactly once.
+__device__ __forceinline__ void epilogue_store_lean(const SpmmArgs& a, int64_t row, int c4, float4 v, uint64_t strm) {
+  if (a.bias) {
+    const int64_t c = 4 * (int64_t)c4;
+    v.x = __fadd_rn(v.x, __ldg(a.bias + c));
+    v.y = __fadd_rn(v.y, (c + 1 < a.F) ? __ldg(a.bias + c + 1) : 0.f);
+    v.z = __fadd_rn(v.z, (c + 2 < a.F) ? __ldg(a.bias + c + 2) : 0.f);
+    v.w = __fadd_rn(v.w, (c + 3 < a.F) ? __ldg(a.bias + c + 3) : 0.f);
+  }
+  if (a.act == GCG_ACT_RELU) {
+    v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+  }
+  stg_f4_stream(reinterpret_cast<float4*>(a.C + row * a.ldc + 4 * (int64_t)c4), v, strm);
+}
+
+// One warp = one span.  VPLMAX float4 per lane and row, D = pipeline depth (ring slots / register rows),
+// SMEM = transport.  Iteration t issues the gather of non-zero t and consumes non-zero t - (D - 1); the loop
+// runs D - 1 iterations past the span's last non-zero so that the last rows drain through the same (single)
+// row-flush site.
+template <int VPLMAX, int D, bool SMEM, bool LEAN>
+__device__ __forceinline__ void spmm_stream_body(const SpmmArgs& a, const StreamSpan* __restrict__ spans, int n_spans,
+                                                 const int* __restrict__ vptr, const int* __restrict__ vdst, int n_v,
+                                                 int warps_per_cta) {
+  extern __shared__ __align__(128) uint8_t smem_dyn[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int si = blockIdx.x * warps_per_cta + warp;
+  if (si >= n_spans) return;
+  const int4 spv = __ldg(reinterpret_cast<const int4*>(spans) + si);
+  const int v_beg = spv.x, v_end = spv.y, f4_beg = spv.z, f4_cnt = spv.w;
+  const uint64_t keep = policy_evict_last(), strm = policy_evict_first();
+  const unsigned full = 0xffffffffu;
+
+  bool cv[VPLMAX];
+#pragma unroll
+  for (int j = 0; j < VPLMAX; ++j) cv[j] = (lane + 32 * j) < f4_cnt;
+  const float4* __restrict__ Bp = reinterpret_cast<const float4*>(a.B) + f4_beg + lane;
+  const int64_t ldb4 = a.ldb >> 2;
+  const int k0 = __ldg(vptr + v_beg), k1 = __ldg(vptr + v_end);
+  const int nnz_total = a.nnz_total;
+
+  // chunk caches: 32 consecutive column indices (producer side), values (consumer side) and virtual-row
+  // boundaries / destinations, each with its successor prefetched
+  auto ld_idx = [&](int base) { const int q = base + lane; return q < nnz_total ? ldg_i32_stream(a.indices + q, strm) : 0; };
+  auto ld_val = [&](int base) { const int q = base + lane; return q < nnz_total ? ldg_f32_stream(a.vals + q, strm) : 0.f; };
+  auto ld_vend = [&](int base) { const int q = base + lane + 1; return q <= n_v ? __ldg(vptr + q) : INT_MAX; };
+  auto ld_vdst = [&](int base) { const int q = base + lane; return q < n_v ? __ldg(vdst + q) : 0; };
+  int pb = k0 & ~31;
+  int pidx = ld_idx(pb), pidx_nx = ld_idx(pb + 32);
+  int cb = pb;
+  float cval = ld_val(cb), cval_nx = ld_val(cb + 32);
+  int vb = v_beg;
+  int vend_c = ld_vend(vb), vend_nx = ld_vend(vb + 32);
+  int vdst_c = ld_vdst(vb), vdst_nx = ld_vdst(vb + 32);
+  int v = v_beg;
+  int vstart = k0;
+  int vend = __shfl_sync(full, vend_c, 0);
+
+  float4 acc[VPLMAX];
+#pragma unroll
+  for (int j = 0; j < VPLMAX; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  auto flush_row = [&]() {      // virtual row v is complete: store it, move on to v + 1
+    const int dst = __shfl_sync(full, vdst_c, v - vb);
+    if (dst >= 0) {
+      // plain accumulation of an empty row is a no-op (column-blocked products visit mostly empty rows)
+      const bool skip = (vstart == vend) && a.accumulate && !a.bias && a.act == GCG_ACT_IDENTITY && !a.gate;
+      if (!skip) {
+#pragma unroll
+        for (int j = 0; j < VPLMAX; ++j)
+          if (cv[j]) {
+            if (LEAN) epilogue_store_lean(a, dst, f4_beg + lane + 32 * j, acc[j], strm);
+            else epilogue_store(a, dst, f4_beg + lane + 32 * j, acc[j], strm);
+          }
+      }
+    } else {
+      float4* out = reinterpret_cast<float4*>(a.part + (int64_t)(~dst) * a.ldc) + f4_beg + lane;
+#pragma unroll
+      for (int j = 0; j < VPLMAX; ++j)
+        if (cv[j]) out[32 * j] = acc[j];             // re-read soon by finalize: default policy
+    }
+#pragma unroll
+    for (int j = 0; j < VPLMAX; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    ++v;
+    if (v - vb == 32) {
+      vb += 32;
+      vend_c = vend_nx; vdst_c = vdst_nx;
+      vend_nx = ld_vend(vb + 32); vdst_nx = ld_vdst(vb + 32);
+    }
+    vstart = vend;
+    vend = __shfl_sync(full, vend_c, v - vb);
+  };
+
+  if (SMEM) {
+    // ---- shared-memory ring: slot index is a run-time counter, the loop body exists once
+    constexpr uint32_t SLOT = VPLMAX * 512;
+    const uint32_t ring = smem_u32(smem_dyn) + (uint32_t)warp * (D * SLOT) + lane * 16;
+    uint32_t ps = 0, cs = (D > 1) ? SLOT : 0;          // producer slot offset; consumer runs one slot ahead of it
+    for (int t = k0; t < k1 + D; ++t) {
+      if (t < k1) {
+        if (t >= pb + 32) { pb += 32; pidx = pidx_nx; pidx_nx = ld_idx(pb + 32); }
+        const int col = __shfl_sync(full, pidx, t - pb);
+        const float4* src = Bp + (int64_t)col * ldb4;
+#pragma unroll
+        for (int j = 0; j < VPLMAX; ++j)
+          if (cv[j]) cp_async16(ring + ps + j * 512, src + 32 * j, keep);
+      }
+      cp_async_commit();                                // one group per iteration (possibly empty)
+      const int c = t - (D - 1);
+      if (c >= k0) {
+        while (v < v_end && c >= vend) flush_row();     // row boundaries, empty rows, and the tail at c == k1
+        if (c < k1) {
+          if (c >= cb + 32) { cb += 32; cval = cval_nx; cval_nx = ld_val(cb + 32); }
+          const float val = __shfl_sync(full, cval, c - cb);
+          cp_async_wait<D - 1>();
+          float4 xv[VPLMAX];
+#pragma unroll
+          for (int j = 0; j < VPLMAX; ++j)
+            if (cv[j]) xv[j] = lds_f4(ring + cs + j * 512);
+#pragma unroll
+          for (int j = 0; j < VPLMAX; ++j)
+            if (cv[j]) acc[j] = f4_axpy_exact(acc[j], val, xv[j]);
+        }
+      }
+      ps = (ps + SLOT == D * SLOT) ? 0u : ps + SLOT;
+      cs = (cs + SLOT == D * SLOT) ? 0u : cs + SLOT;
+    }
+  } else {
+    // ---- register pipeline: D rows rotate through statically indexed registers (unrolled by D)
+    float4 x[D][VPLMAX];
+    for (int base = k0; base < k1 + D; base += D) {
+#pragma unroll
+      for (int u = 0; u < D; ++u) {
+        const int t = base + u;
+        if (t < k1) {
+          if (t >= pb + 32) { pb += 32; pidx = pidx_nx; pidx_nx = ld_idx(pb + 32); }
+          const int col = __shfl_sync(full, pidx, t - pb);
+          const float4* src = Bp + (int64_t)col * ldb4;
+#pragma unroll
+          for (int j = 0; j < VPLMAX; ++j)
+            if (cv[j]) x[u][j] = ldg_f4_keep(src + 32 * j, keep);
+        }
+        const int c = t - (D - 1);
+        if (c >= k0) {
+          while (v < v_end && c >= vend) flush_row();
+          if (c < k1) {
+            if (c >= cb + 32) { cb += 32; cval = cval_nx; cval_nx = ld_val(cb + 32); }
+            const float val = __shfl_sync(full, cval, c - cb);
+            const int cu = (u + 1 == D) ? 0 : u + 1;    // compile-time after unrolling
+#pragma unroll
+            for (int j = 0; j < VPLMAX; ++j)
+              if (cv[j]) acc[j] = f4_axpy_exact(acc[j], val, x[cu][j]);
+          }
+        }
+      }
+    }
+  }
+  while (v < v_end) flush_row();                         // spans made of empty rows only
+}
+
+template <int VPLMAX, int D, int WARPS, int MINB, bool SMEM, bool LEAN>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
+spmm_stream_kernel(const SpmmArgs a, const StreamSpan* __restrict__ spans, int n_spans, const int* __restrict__ vptr,
+                   const int* __restrict__ vdst, int n_v) {
+  spmm_stream_body<VPLMAX, D, SMEM, LEAN>(a, spans, n_spans, vptr, vdst, n_v, WARPS);
+}
+
+// ------------------------------------------------------------------------------------------ host side
+template <int VPLMAX, int D, int WARPS, int MINB, bool SMEM, bool LEAN>
+static cudaError_t launch_stream_epi(const SpmmArgs& a, const StreamSchedule& s, const StreamState& ss, cudaStream_t st) {
+  auto kern = spmm_stream_kernel<VPLMAX, D, WARPS, MINB, SMEM, LEAN>;
+  const int smem_bytes = SMEM ? WARPS * D * VPLMAX * 512 : 0;
+  if (SMEM) {
+    static bool attr_set = false;       // per instantiation
+    if (!attr_set) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+      if (e != cudaSuccess) return e;
+      attr_set = true;
+    }
+  }
+  const unsigned grid = (unsigned)ceil_div(s.n_spans, WARPS);
+  kern<<<grid, WARPS * 32, smem_bytes, st>>>(a, s.d_spans, s.n_spans, ss.d_vptr, ss.d_vdst, (int)ss.n_v);
+  return cudaGetLastError();
+}
+
+template <int VPLMAX, int D, int WARPS, int MINB, bool SMEM>
+static cudaError_t launch_stream(const SpmmArgs& a, const StreamSchedule& s, const StreamState& ss, cudaStream_t st) {
+  const bool lean = a.act <= GCG_ACT_RELU && !a.gate && !a.accumulate;
+  return lean ? launch_stream_epi<VPLMAX, D, WARPS, MINB, SMEM, true>(a, s, ss, st)
+              : launch_stream_epi<VPLMAX, D, WARPS, MINB, SMEM, false>(a, s, ss, st);
+}
+
+// (VPLMAX, variant) -> kernel.  Variant 0 picks the measured default of the width class.
+//   variants 1..4: shared-memory ring;   5..8: register pipeline
+static cudaError_t dispatch_stream(int vplmax, int variant, const SpmmArgs& a, const StreamSchedule& s,
+                                   const StreamState& ss, cudaStream_t st, bool* found) {
+  *found = true;
+#define GCG_ST(V, VAR, D, W, MB, SM) \
+  if (vplmax == V && variant == VAR) return launch_stream<V, D, W, MB, SM>(a, s, ss, st);
+  // ---- 1 float4 per lane (<= 128 floats per panel)
+  GCG_ST(1, 1, 16, 16, 1, true)  GCG_ST(1, 2, 12, 16, 1, true)  GCG_ST(1, 3, 8, 16, 2, true)
+  GCG_ST(1, 5, 8, 8, 3, false)   GCG_ST(1, 6, 4, 8, 4, false)
+  // ---- 2 float4 per lane (<= 256 floats)
+  GCG_ST(2, 1, 12, 16, 1, true)  GCG_ST(2, 2, 8, 16, 1, true)   GCG_ST(2, 3, 6, 16, 2, true)
+  GCG_ST(2, 5, 4, 8, 3, false)   GCG_ST(2, 6, 2, 8, 4, false)
+  // ---- 3 float4 per lane (<= 384 floats)
+  GCG_ST(3, 1, 8, 16, 1, true)   GCG_ST(3, 2, 6, 16, 1, true)
+  GCG_ST(3, 5, 3, 8, 3, false)   GCG_ST(3, 6, 2, 8, 3, false)
+  // ---- 4 float4 per lane (<= 512 floats)
+  GCG_ST(4, 1, 6, 16, 1, true)   GCG_ST(4, 2, 5, 16, 1, true)
+  GCG_ST(4, 5, 3, 8, 2, false)   GCG_ST(4, 6, 2, 8, 2, false)
+  // ---- 5 float4 per lane (<= 640 floats: hidden 600)
+  GCG_ST(5, 1, 5, 16, 1, true)   GCG_ST(5, 2, 4, 16, 1, true)   GCG_ST(5, 3, 8, 8, 1, true)   GCG_ST(5, 4, 6, 12, 1, true)
+  GCG_ST(5, 5, 3, 8, 2, false)   GCG_ST(5, 7, 2, 8, 2, false)
+  // ---- 8 float4 per lane (<= 1024 floats: 1024 regions)
+  GCG_ST(8, 1, 3, 16, 1, true)   GCG_ST(8, 2, 6, 8, 1, true)
+  GCG_ST(8, 5, 2, 8, 2, false)
+#undef GCG_ST
+  *found = false;
+  return cudaSuccess;
+}
+
+static int default_variant(int vplmax) { return 1; }
+
+static int build_vrows(const gcg_plan* p, StreamState* s) {
+  const int64_t n = p->n_rows;
+  const int32_t T = p->long_thresh;
+  const std::vector<int32_t>& ip = p->h_indptr;
+  std::vector<int32_t> vdst;
+  s->h_vptr.clear();
+  s->h_row_v.assign(n + 1, 0);
+  s->h_vptr.reserve(n + p->n_seg + 1);
+  vdst.reserve(n + p->n_seg);
+  int32_t seg = 0;
+  for (int64_t r = 0; r < n; ++r) {
+    s->h_row_v[r] = (int32_t)vdst.size();
+    const int32_t b = ip[r], e = ip[r + 1];
+    if (e - b > T) {
+      for (int32_t k = b; k < e; k += T) {
+        s->h_vptr.push_back(k);
+        vdst.push_back(~seg);
+        ++seg;
+      }
+    } else {
+      s->h_vptr.push_back(b);
+      vdst.push_back((int32_t)r);
+    }
+  }
+  s->h_row_v[n] = (int32_t)vdst.size();
+  s->h_vptr.push_back(ip[n]);
+  s->n_v = (int64_t)vdst.size();
+  if (seg != p->n_seg) { set_error("stream plan: segment count mismatch (%d vs %lld)", seg, (long long)p->n_seg); return GCG_ERR_SHAPE; }
+  GCG_CUDA(cudaMalloc(&s->d_vptr, sizeof(int32_t) * (s->n_v + 1)));
+  GCG_CUDA(cudaMalloc(&s->d_vdst, sizeof(int32_t) * std::max<int64_t>(1, s->n_v)));
+  GCG_CUDA(cudaMemcpy(s->d_vptr, s->h_vptr.data(), sizeof(int32_t) * (s->n_v + 1), cudaMemcpyHostToDevice));
+  if (s->n_v > 0) GCG_CUDA(cudaMemcpy(s->d_vdst, vdst.data(), sizeof(int32_t) * s->n_v, cudaMemcpyHostToDevice));
+  return GCG_OK;
+}
+
+static int build_schedule(const gcg_plan* p, StreamState* s, int f4_total, int span_nnz, StreamSchedule* out) {
+  std::vector<StreamSpan> spans;
+  const int64_t n = p->n_rows;
+  std::vector<int32_t> one_rows = {0, (int32_t)n};
+  std::vector<int32_t> one_panels = {1};
+  const std::vector<int32_t>& brows = s->blk_rows.empty() ? one_rows : s->blk_rows;
+  const std::vector<int32_t>& bpan = s->blk_rows.empty() ? one_panels : s->blk_panels;
+  int vplmax = 1;
+  const size_t nb = bpan.size();
+  for (size_t b = 0; b < nb; ++b) {
+    const int32_t r0 = brows[b], r1 = brows[b + 1];
+    if (r1 <= r0) continue;
+    const bool interleave = bpan[b] < 0;
+    int np = std::max(1, std::abs(bpan[b]));
+    // panel width: a multiple of 8 float4 (128 B) unless one panel covers the row
+    int pw = (int)ceil_div(f4_total, np);
+    if (np > 1) pw = (int)ceil_div(pw, 8) * 8;
+    pw = std::min(pw, 256);                            // VPLMAX <= 8
+    np = (int)ceil_div(f4_total, pw);
+    const int vpl = (int)ceil_div(std::min(pw, f4_total), 32);
+    vplmax = std::max(vplmax, vpl);
+    const int32_t v0 = s->h_row_v[r0], v1 = s->h_row_v[r1];
+    // spans of the block for one panel (the same cut for every panel)
+    std::vector<std::pair<int32_t, int32_t>> cuts;
+    const int64_t target = std::max<int64_t>(32, (int64_t)span_nnz * 5 / std::max(1, std::min(vpl, 5)));
+    int32_t vb = v0;
+    while (vb < v1) {
+      int32_t ve = vb + 1;
+      const int64_t kb = s->h_vptr[vb];
+      while (ve < v1 && (int64_t)s->h_vptr[ve + 1] - kb <= target && ve - vb < 4096) ++ve;
+      cuts.push_back({vb, ve});
+      vb = ve;
+    }
+    if (interleave) {
+      for (auto& c : cuts)
+        for (int q = 0; q < np; ++q)
+          spans.push_back({c.first, c.second, q * pw, std::min(pw, f4_total - q * pw)});
+    } else {
+      for (int q = 0; q < np; ++q)
+        for (auto& c : cuts)
+          spans.push_back({c.first, c.second, q * pw, std::min(pw, f4_total - q * pw)});
+    }
+  }
+  out->f4_total = f4_total;
+  out->vplmax = vplmax == 6 || vplmax == 7 ? 8 : vplmax;
+  out->n_spans = (int)spans.size();
+  out->d_spans = nullptr;
+  if (!spans.empty()) {
+    GCG_CUDA(cudaMalloc(&out->d_spans, sizeof(StreamSpan) * spans.size()));
+    GCG_CUDA(cudaMemcpy(out->d_spans, spans.data(), sizeof(StreamSpan) * spans.size(), cudaMemcpyHostToDevice));
+  }
+  return GCG_OK;
+}
+
+int spmm_stream_launch(const gcg_plan* p, SpmmArgs& a, cudaStream_t st) {
+  if (a.f4_total > 256) return 0;
+  gcg_plan* mp = const_cast<gcg_plan*>(p);
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(st, &cap);
+  if (!mp->stream) {
+    if (cap != cudaStreamCaptureStatusNone) {
+      set_error("gcg_spmm_csr_f32: the streaming variant must run once outside CUDA-graph capture (it builds its schedule on first use)");
+      return GCG_ERR_UNSUPPORTED;
+    }
+    mp->stream = new StreamState();
+    const int rc = build_vrows(p, mp->stream);
+    if (rc != GCG_OK) return rc;
+  }
+  StreamState* s = mp->stream;
+  const int span_nnz = g_stream_span_nnz > 0 ? g_stream_span_nnz : 384;
+  StreamSchedule sched;
+  {
+    std::lock_guard<std::mutex> lk(s->mu);
+    const int64_t key = ((int64_t)a.f4_total << 20) + span_nnz;
+    auto it = s->scheds.find(key);
+    if (it == s->scheds.end()) {
+      if (cap != cudaStreamCaptureStatusNone) {
+        set_error("gcg_spmm_csr_f32: streaming schedule for F4=%d missing during CUDA-graph capture", a.f4_total);
+        return GCG_ERR_UNSUPPORTED;
+      }
+      StreamSchedule ns;
+      const int rc = build_schedule(p, s, a.f4_total, span_nnz, &ns);
+      if (rc != GCG_OK) return rc;
+      it = s->scheds.emplace(key, ns).first;
+    }
+    sched = it->second;
+  }
+  if (sched.n_spans == 0) return 1;
+  int variant = g_stream_variant > 0 ? g_stream_variant : default_variant(sched.vplmax);
+  bool found = false;
+  cudaError_t e = dispatch_stream(sched.vplmax, variant, a, sched, *s, st, &found);
+  if (!found) {
+    variant = default_variant(sched.vplmax);
+    e = dispatch_stream(sched.vplmax, variant, a, sched, *s, st, &found);
+    if (!found) return 0;
+  }
+  if (e != cudaSuccess) { set_error("gcg_spmm_csr_f32: streaming launch failed: %s", cudaGetErrorString(e)); return GCG_ERR_CUDA; }
+  count_launch();
+  if (p->n_long > 0) {
+    e = spmm_finalize_launch(a, (int)p->n_long, st);
+    if (e != cudaSuccess) { set_error("gcg_spmm_csr_f32: finalize launch failed: %s", cudaGetErrorString(e)); return GCG_ERR_CUDA; }
+    count_launch();
+  }
+  return 1;
+}
+
+}  // namespace gcg
+
+using namespace gcg;
+
+extern "C" void gcg_spmm_stream_tuning(int variant, int span_nnz) {
+  gcg::g_stream_variant = variant;
+  gcg::g_stream_span_nnz = span_nnz;
+}
+
+extern "C" int gcg_plan_set_schedule(gcg_plan* p, int64_t n_blocks, const int32_t* h_block_rows,
+                                     const int32_t* h_block_panels) {
+  GCG_CHECK_ARG(p != nullptr, "gcg_plan_set_schedule: plan is NULL");
+  GCG_CHECK_ARG(n_blocks >= 0 && (n_blocks == 0 || (h_block_rows && h_block_panels)), "gcg_plan_set_schedule: NULL arrays");
+  if (n_blocks > 0) {
+    GCG_CHECK_SHAPE(h_block_rows[0] == 0 && h_block_rows[n_blocks] == p->n_rows,
+                    "gcg_plan_set_schedule: blocks must cover rows [0, %lld)", (long long)p->n_rows);
+    for (int64_t b = 0; b < n_blocks; ++b) {
+      GCG_CHECK_SHAPE(h_block_rows[b + 1] >= h_block_rows[b], "gcg_plan_set_schedule: block %lld is reversed", (long long)b);
+      GCG_CHECK_ARG(h_block_panels[b] != 0 && std::abs(h_block_panels[b]) <= 64, "gcg_plan_set_schedule: panel count %d", h_block_panels[b]);
+    }
+  }
+  if (!p->stream) {
+    p->stream = new StreamState();
+    const int rc = build_vrows(p, p->stream);
+    if (rc != GCG_OK) return rc;
+  }
+  StreamState* s = p->stream;
+  std::lock_guard<std::mutex> lk(s->mu);
+  // schedules built for the previous blocks are stale; kernels that may still read them must drain first
+  if (!s->scheds.empty()) {
+    GCG_CUDA(cudaDeviceSynchronize());
+    for (auto& kv : s->scheds)
+      if (kv.second.d_spans) cudaFree(kv.second.d_spans);
+    s->scheds.clear();
+  }
+  s->blk_rows.assign(h_block_rows, h_block_rows + (n_blocks > 0 ? n_blocks + 1 : 0));
+  s->blk_panels.assign(h_block_panels, h_block_panels + n_blocks);
+  return GCG_OK;
+}

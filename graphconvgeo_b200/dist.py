@@ -493,6 +493,8 @@ class DistMLPCONV(MLPCONV):
         self.Xd = CSRMatrix.from_host((p, np.ascontiguousarray(ix[ip[part.r0]:ip[part.r1]]),
                                        np.ascontiguousarray(d[ip[part.r0]:ip[part.r1]])),
                                       (part.n_loc, in_size), self.device, 1024)
+        if getattr(self, "keep_host_inputs", False):      # for checkers (host_inputs): the global matrices, model order
+            self._host_inputs = (Xg.to_scipy(), Hg.to_scipy())
         del Xg, Hg
         self._build(self.Xd, Hd, in_size, out_size)
         self.ti = {}
@@ -542,9 +544,14 @@ class DistMLPCONV(MLPCONV):
             if works is not None:
                 for g in ly.grads.values():
                     works.append(dist.all_reduce(g, group=self.group, async_op=True))
+        from .mlpconv import DropoutLayer
         grad, preact = G, False
         for i in range(len(self.layers) - 1, -1, -1):
             ly = self.layers[i]
+            if isinstance(ly, DropoutLayer):          # same rule as the single-GPU loop: the mask scales the
+                grad = ly.backward(grad)              # gradient and act' of the layer below is applied there
+                preact = False
+                continue
             prev = self.layers[i - 1] if i > 0 else None
             mask = None
             if prev is not None and type(prev) in (L.SparseConvolutionDenseLayer, L.ConvolutionDenseLayer) \
@@ -602,6 +609,12 @@ class DistMLPCONV(MLPCONV):
         ti = self._partition(dataset_partition)
         y = torch.from_numpy(np.ascontiguousarray(np.asarray(y_true)[ti.sel], dtype=np.int32)).to(self.device)
         return self.f_val(y, ti)[1]
+
+    def host_inputs(self):
+        """the GLOBAL (X, A_hat) in model order; set ``keep_host_inputs = True`` before prepare()"""
+        if getattr(self, "_host_inputs", None) is None:
+            raise RuntimeError("DistMLPCONV.host_inputs: set keep_host_inputs = True before prepare()")
+        return self._host_inputs
 
     def node_rows(self, t):
         """local slab -> full matrix in ORIGINAL node order (all-gathered; for tests)."""

@@ -353,7 +353,8 @@ class _ConvBase(DenseLayer):
         """buffer for a dense SpMM operand: in row-partitioned mode it is the local slab of the
         (shared, transient) all-gather buffer, so no staging copy is needed"""
         if hasattr(self.H, "operand"):
-            return self.H.operand(key, n_cols)
+            return self.H.operand((id(self), key), n_cols)      # one gather buffer per layer and role: every
+                                                                # operand of a step stays inspectable afterwards
         return self._mat(key, n_rows, n_cols)
 
     def _target(self, target_indices):

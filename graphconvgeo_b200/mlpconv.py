@@ -364,6 +364,11 @@ class MLPCONV:
         a = t.detach().cpu().numpy()
         return a if self.node_order is None else a[self.node_inverse]
 
+    def host_inputs(self):
+        """(X, A_hat) as scipy CSR matrices in the MODEL'S node order (after the locality reordering) -- what a
+        checker needs to recompute rows of any layer on the host."""
+        return self.Xd.to_scipy(), self.l_hid1.H.to_scipy()
+
     def get_param_values(self):
         return L.get_all_param_values(self.l_out)
 

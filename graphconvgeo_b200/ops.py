@@ -204,6 +204,14 @@ def gemm(A, B, out=None, transA=False, transB=False, beta=0.0, bias=None, act="i
         raise ValueError("gemm: out has shape %s, expected %s" % (tuple(out.shape), (M, N)))
     if M == 0 or N == 0:
         return out
+    if K == 0:                    # empty contraction (e.g. a rank without target rows): op(A).op(B) = 0
+        if beta == 0.0:
+            out.zero_()
+        elif beta != 1.0:
+            out.mul_(beta)
+        if bias is not None or act != "identity" or mask is not None:
+            raise ValueError("gemm: K == 0 with an epilogue is not supported")
+        return out
     cp, ldc = _mat(out, "out")
     mp, ldm = (None, 0) if mask is None else _mat(mask, "mask")
     if mode is None:
@@ -236,6 +244,8 @@ def colsum(X, out=None):
     n, F = X.shape
     if out is None:
         out = torch.empty(F, dtype=torch.float32, device=X.device)
+    if n == 0 or F == 0:          # a rank that owns no rows: the sum over nothing (an empty tensor has a NULL pointer)
+        return out.zero_()
     ws, wsb = scratch.get(L.gcg_colsum_workspace_bytes(n, F), X.device)
     _lib.check(L.gcg_colsum_f32(xp, ld, n, F, _vec(out, "out"), ws, wsb, _stream()), "gcg_colsum_f32")
     return out
@@ -247,6 +257,8 @@ def act_bwd(dA, A, act, out=None):
     ap, lda = _mat(A, "A")
     if out is None:
         out = alloc_mat(dA.shape[0], dA.shape[1], dA.device)
+    if dA.shape[0] == 0 or dA.shape[1] == 0:
+        return out
     op, ldo = _mat(out, "out")
     _lib.check(L.gcg_act_bwd_f32(dp, ldd, ap, lda, op, ldo, dA.shape[0], dA.shape[1], _lib.act_code(act),
                                  _stream()), "gcg_act_bwd_f32")
@@ -306,6 +318,10 @@ def scatter_rows(G, pos_ptr, pos_idx, n_rows, out=None):
     Cc = G.shape[1]
     if out is None:
         out = alloc_mat(n_rows, Cc, G.device)
+    if n_rows == 0 or Cc == 0:
+        return out
+    if G.shape[0] == 0:           # no target rows on this rank: nothing is scattered, the gradient slab is zero
+        return out.zero_()
     op, ldo = _mat(out, "out")
     _lib.check(L.gcg_scatter_rows_f32(gp, ldg, _vec(pos_ptr, "pos_ptr", torch.int32),
                                       _vec(pos_idx, "pos_idx", torch.int32), n_rows, Cc, op, ldo, _stream()),

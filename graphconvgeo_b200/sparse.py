@@ -111,6 +111,22 @@ class CSRMatrix:
         keys = ["n_rows", "n_cols", "nnz", "n_long_rows", "n_segments", "max_degree", "long_row_threshold"]
         return dict(zip(keys, list(info)[:7]))
 
+    def set_schedule(self, block_rows=None, block_panels=None):
+        """Row-block x column-panel schedule of the streaming SpMM (gcg_plan_set_schedule).  ``block_rows``:
+        ascending row offsets [0, ..., n_rows]; ``block_panels``: panels per block (> 0 panel-major inside the
+        block, < 0 interleaved).  ``None`` restores whole rows in one block."""
+        if block_rows is None:
+            _lib.check(_lib.lib().gcg_plan_set_schedule(self.plan, 0, None, None), "gcg_plan_set_schedule")
+            self.schedule = None
+            return
+        br = np.ascontiguousarray(np.asarray(block_rows), dtype=np.int32)
+        bp = np.ascontiguousarray(np.asarray(block_panels), dtype=np.int32)
+        if len(br) != len(bp) + 1:
+            raise ValueError("set_schedule: need len(block_rows) == len(block_panels) + 1")
+        _lib.check(_lib.lib().gcg_plan_set_schedule(self.plan, len(bp), _np_ptr(br), _np_ptr(bp)),
+                   "gcg_plan_set_schedule")
+        self.schedule = (br, bp)
+
     def workspace_bytes(self, ldc):
         return int(_lib.lib().gcg_plan_workspace_bytes(self.plan, int(ldc)))
 
@@ -227,6 +243,51 @@ class CSRMatrix:
                                                    _np_ptr(cm) if cm is not None else None, _np_ptr(oip),
                                                    _np_ptr(oix), _np_ptr(od)), "gcg_csr_permute_host")
         return CSRMatrix.from_host((oip, oix, od), self.shape, self.device, self.long_row_threshold)
+
+
+def l2_schedule(A: "CSRMatrix", F, budget_bytes=48 << 20, min_panel_floats=128,
+                block_rows_candidates=(16384, 65536, 262144), report=None):
+    """Row-block x column-panel schedule for the streaming SpMM of ``A`` against an [n_cols, F] operand
+    (CSRMatrix.set_schedule), chosen by a traffic model evaluated on the matrix itself.
+
+    For a block of consecutive rows, D = distinct columns it references.  Split into p column panels, the
+    block gathers from D * 4F/p bytes per panel; when that fits ``budget_bytes`` of L2 every repeated reference
+    hits, otherwise only budget / working-set of them.  Per candidate block height the model sums first
+    touches, missed repeats, the CSR re-read per panel and a fixed per-non-zero cost per extra panel pass,
+    and the cheapest candidate wins.  Index analysis (sort / unique of nnz keys) runs with torch on the
+    matrix's device -- plumbing, like the rest of the one-off plan preparation."""
+    n, ncols = A.shape
+    dev = A.device
+    row_bytes = 4.0 * F
+    deg = (A.indptr[1:] - A.indptr[:-1]).to(torch.int64)
+    rows = torch.repeat_interleave(torch.arange(n, device=dev, dtype=torch.int64), deg)
+    cols = A.indices.to(torch.int64)
+    max_panels = max(1, int(F) // int(min_panel_floats))
+    best = None
+    for R in block_rows_candidates:
+        nb = -(-n // R)
+        blk = rows // R
+        uniq = torch.unique(blk * ncols + cols)
+        D = torch.bincount(uniq // ncols, minlength=nb).double()
+        del uniq
+        nnz_b = torch.bincount(blk, minlength=nb).double()
+        panels = torch.clamp(torch.ceil(D * row_bytes / budget_bytes), 1, max_panels)
+        ws = D * row_bytes / panels
+        hit = torch.clamp(budget_bytes / torch.clamp(ws, min=1.0), max=1.0)
+        est = (D * row_bytes + (nnz_b - D) * row_bytes * (1.0 - hit) + nnz_b * 8.0 * panels
+               + nnz_b * 256.0 * (panels - 1.0)).sum().item()
+        cand = dict(block_rows=R, est_bytes=est, panels=panels.to(torch.int32).cpu().numpy(),
+                    distinct=float(D.sum().item()))
+        if report is not None:
+            report.append({k: (v if k != "panels" else np.bincount(v).tolist()) for k, v in cand.items()})
+        if best is None or est < best["est_bytes"]:
+            best = cand
+        if nb == 1:
+            break
+    R = best["block_rows"]
+    nb = -(-n // R)
+    br = np.minimum(np.arange(nb + 1, dtype=np.int64) * R, n).astype(np.int32)
+    return br, best["panels"].astype(np.int32)
 
 
 def as_csr(x, device="cuda", long_row_threshold=256) -> CSRMatrix:

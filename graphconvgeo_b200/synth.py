@@ -97,11 +97,23 @@ def powerlaw_graph(n, avg_deg, seed=77, alpha=1.5, communities=None, intra=0.8, 
 
 
 # --------------------------------------------------------------------- TF-IDF
-def tfidf_matrix(n, vocab, mean_terms, seed=77, zipf_s=1.1):
+LOCAL_TERM_FRACTION = 0.15      # share of a user's term draws that come from the vocabulary of the user's city
+LOCAL_TERMS = 2048              # size of a city's own vocabulary slice
+
+
+def _local_columns(ranks, city, vocab, xp):
+    """term id of a 'local' draw: the city's own slice of the vocabulary (place names, dialect words --
+    what makes text geolocation possible at all), Zipf-ranked inside the slice"""
+    base = (city * 7919 * 64) % vocab
+    return (base + (ranks % LOCAL_TERMS) * 17) % vocab
+
+
+def tfidf_matrix(n, vocab, mean_terms, seed=77, zipf_s=1.1, city=None):
     """CSR float32 [n, vocab]: binary tf, smooth idf (ln((1+n)/(1+df))+1), rows L2-normalised
     -- sklearn TfidfVectorizer(binary=True, use_idf=True, norm='l2') as configured at
     data.py:254-256,386-389.  Row lengths ~ max(1, LogNormal) with the given mean; term ids
-    ~ truncated Zipf(zipf_s), de-duplicated per row."""
+    ~ truncated Zipf(zipf_s), de-duplicated per row.  With ``city`` (one id per row) a fixed share of the
+    draws is redirected to the city's own vocabulary slice, so the text carries location signal."""
     rng = np.random.RandomState(seed + 1)
     sigma = 0.6
     mu = np.log(mean_terms) - 0.5 * sigma * sigma
@@ -115,6 +127,9 @@ def tfidf_matrix(n, vocab, mean_terms, seed=77, zipf_s=1.1):
     cols = np.searchsorted(cdf, rng.random_sample(total)).astype(np.int64)
     np.minimum(cols, vocab - 1, out=cols)
     rows = np.repeat(np.arange(n, dtype=np.int64), lens)
+    if city is not None:
+        local = rng.random_sample(total) < LOCAL_TERM_FRACTION
+        cols = np.where(local, _local_columns(cols, np.asarray(city, dtype=np.int64)[rows], vocab, np), cols)
     key = np.unique(rows * vocab + cols)
     rows, cols = key // vocab, key % vocab
     df = np.bincount(cols, minlength=vocab).astype(np.float64)
@@ -182,7 +197,7 @@ def make_workload(name="geotext", seed=77, community=True, scale=1.0, **override
     locs, city = city_locations(n, cfg["n_cities"], seed)
     adj = powerlaw_graph(n, cfg["avg_deg"], seed, communities=city if community else None)
     a_hat = build_ahat_host(adj)
-    X = tfidf_matrix(n, cfg["vocab"], cfg["terms"], seed)
+    X = tfidf_matrix(n, cfg["vocab"], cfg["terms"], seed, city=city)
     y_train, y_other, med = assign_classes(locs[:n_train], locs[n_train:], cfg["bucket"])
     Y = np.concatenate([y_train, y_other]).astype(np.int64)
     return Workload(
@@ -237,7 +252,7 @@ def _torch_graph(n, avg_deg, gen, device, city=None, intra=0.8, alpha=1.5):
     return indptr.to(torch.int32), cols.to(torch.int32)
 
 
-def _torch_tfidf(n, vocab, mean_terms, gen, device, zipf_s=1.1):
+def _torch_tfidf(n, vocab, mean_terms, gen, device, zipf_s=1.1, city=None):
     import torch
     sigma = 0.6
     mu = float(np.log(mean_terms) - 0.5 * sigma * sigma)
@@ -253,6 +268,9 @@ def _torch_tfidf(n, vocab, mean_terms, gen, device, zipf_s=1.1):
     for s in range(0, total, step):
         e = min(total, s + step)
         c = torch.searchsorted(cdf, torch.rand(e - s, generator=gen, device=device, dtype=torch.float64)).clamp_(max=vocab - 1)
+        if city is not None:
+            local = torch.rand(e - s, generator=gen, device=device) < LOCAL_TERM_FRACTION
+            c = torch.where(local, _local_columns(c, city[rows[s:e]], vocab, torch), c)
         keys.append(rows[s:e] * vocab + c)
     del rows
     key = torch.unique(torch.cat(keys))
@@ -269,27 +287,40 @@ def _torch_tfidf(n, vocab, mean_terms, gen, device, zipf_s=1.1):
     return indptr.to(torch.int32), cols.to(torch.int32), vals
 
 
-def make_workload_device(name="twitter-world", device="cuda", seed=77, community=True, scale=1.0, **overrides):
-    """Same shapes as make_workload, generated with torch on ``device``.  Returns a Workload whose
-    X / A_hat are ``CSRMatrix`` objects already resident on the device (their host copies are
-    materialised lazily, only where the product needs them: transposes and row gathers)."""
+def make_raw_device(name="twitter-world", device="cuda", seed=77, community=True, scale=1.0, **overrides):
+    """The seeded raw inputs of a workload, generated with torch on ``device`` and touching nothing of
+    libgcg.so: binary adjacency pattern (indptr, indices int32), TF-IDF X (indptr, indices int32, values
+    float32) and coordinates (host float64).  ``make_workload_device`` builds A_hat / labels from these with
+    the product's entry points; ``bench.py --impl reference`` builds them with the oracle's (tensormain.py:
+    170-180, kdtree.py) so that the reference arm runs the same workload without loading the product."""
     import torch
-    from . import ops
-    from .sparse import CSRMatrix, _np_ptr
-    from . import _lib
     cfg = dict(WORKLOADS[name])
     cfg.update(overrides)
     if scale != 1.0:
         for k in ("n_train", "n_dev", "n_test", "vocab"):
             cfg[k] = max(8, int(round(cfg[k] * scale)))
         cfg["n_cities"] = max(4, int(round(cfg["n_cities"] * max(scale, 0.05))))
-    n_train, n_dev, n_test = cfg["n_train"], cfg["n_dev"], cfg["n_test"]
-    n = n_train + n_dev + n_test
+    n = cfg["n_train"] + cfg["n_dev"] + cfg["n_test"]
     dev = torch.device(device)
     gen = torch.Generator(device=dev).manual_seed(seed)
     locs, city = city_locations(n, cfg["n_cities"], seed)
     city_t = torch.from_numpy(city).to(dev) if community else None
     ip, ix = _torch_graph(n, cfg["avg_deg"], gen, dev, city=city_t)
+    xip, xix, xv = _torch_tfidf(n, cfg["vocab"], cfg["terms"], gen, dev,
+                                city=torch.from_numpy(city).to(dev))
+    return cfg, n, locs, (ip, ix), (xip, xix, xv)
+
+
+def make_workload_device(name="twitter-world", device="cuda", seed=77, community=True, scale=1.0, **overrides):
+    """Same shapes as make_workload, generated with torch on ``device``.  Returns a Workload whose
+    X / A_hat are ``CSRMatrix`` objects already resident on the device (their host copies are
+    materialised lazily, only where the product needs them: transposes and row gathers)."""
+    import torch
+    from .sparse import CSRMatrix, _np_ptr
+    from . import _lib
+    cfg, n, locs, (ip, ix), (xip, xix, xv) = make_raw_device(name, device, seed, community, scale, **overrides)
+    n_train, n_dev, n_test = cfg["n_train"], cfg["n_dev"], cfg["n_test"]
+    dev = torch.device(device)
     if dev.type == "cuda":
         # A_hat through the product's device builder (gcg_ahat_*_device): float64 normalise, cast
         from .sparse import build_ahat_device
@@ -305,7 +336,6 @@ def make_workload_device(name="twitter-world", device="cuda", seed=77, community
                    "gcg_ahat_build_host")
         a_hat = CSRMatrix.from_host((oip, oix, ov), (n, n), dev)
     del ip, ix
-    xip, xix, xv = _torch_tfidf(n, cfg["vocab"], cfg["terms"], gen, dev)
     X = CSRMatrix(xip, xix, xv, (n, cfg["vocab"]), long_row_threshold=1024)
     y_train, y_other, med = assign_classes(locs[:n_train], locs[n_train:], cfg["bucket"])
     Y = np.concatenate([y_train, y_other]).astype(np.int64)

@@ -103,7 +103,11 @@ int gcg_plan_info(const gcg_plan* plan, int64_t* info);
  * 16-byte aligned B/C and ldb, ldc multiples of 4 with ld >= round_up(F, 4)
  * (pad columns of C are then overwritten with unspecified values); anything
  * else takes the scalar path.
- * panel_cols: -1 = whole rows per warp with the gathered rows staged in shared memory by
+ * panel_cols: -2 = nnz-balanced streaming variant (csrc/gcg_spmm_stream.cu): every warp executes one "span" of
+ * consecutive rows holding an equal share of the non-zeros, gathered rows travel through a deep per-warp
+ * pipeline (cp.async shared-memory ring or rotating registers), spans follow the plan's row-block x column-panel
+ * schedule (gcg_plan_set_schedule).  Builds its tables on first use -> call once outside graph capture.
+ * -1 = whole rows per warp with the gathered rows staged in shared memory by
  * cp.async.bulk (TMA) copies into a per-warp ring (deepest memory-level parallelism; F <= 1024);
  * 0 = whole rows per warp gathered straight into registers; >0 = process the feature dimension in
  * column panels of that many floats, panel-major over the grid, so that one
@@ -115,6 +119,19 @@ int gcg_spmm_csr_f32(const gcg_plan* plan, const float* B, int64_t ldb, int64_t 
                      const float* carry, int64_t ld_carry, float* conv_out,
                      int64_t ld_conv, int32_t panel_cols, void* workspace,
                      int64_t workspace_bytes, void* stream);
+
+/* Row-block x column-panel schedule of the streaming variant (panel_cols = -2).  Rows [block_rows[b],
+ * block_rows[b+1]) form block b, processed in |block_panels[b]| column panels: > 0 panel-major inside the block
+ * (all rows of panel 0, then panel 1, ...: the block's gathered columns x panel bytes stay L2-resident -- 2-D
+ * tiling for communities larger than L2), < 0 interleaved (the panels of the same rows run side by side in one
+ * CTA).  n_blocks = 0 restores the default (one block, whole rows).  Host arrays; the plan copies them.
+ * Results are bit-identical for every schedule (each output element still sums its row in CSR order).
+ * Replaces: nothing in the reference; B200-side preparation for S.dot, lasagne_layers.py:67,84. */
+int gcg_plan_set_schedule(gcg_plan* plan, int64_t n_blocks, const int32_t* h_block_rows,
+                          const int32_t* h_block_panels);
+/* experiment knobs of the streaming variant: kernel variant (0 = default of the width class; 1-4 shared-memory
+ * ring depths, 5-8 register pipelines) and non-zeros per span (0 = 384) */
+void gcg_spmm_stream_tuning(int variant, int span_nnz);
 
 /* ------------------------------------------------------------------- GEMM */
 

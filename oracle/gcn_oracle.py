@@ -33,9 +33,11 @@ def build_ahat(adj, dtype="float32"):
     ``adj`` is the (binary, symmetric) user-user adjacency as any scipy sparse
     matrix; it is not modified.
     """
-    adj = sp.csr_matrix(adj, dtype=np.float64, copy=True).tolil()
-    adj.setdiag(1)                                      # tensormain.py:172
-    adj = adj.tocsr()
+    import warnings
+    adj = sp.csr_matrix(adj, dtype=np.float64, copy=True)   # nx.adjacency_matrix gave the reference a CSR matrix (:170)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", sp.SparseEfficiencyWarning)
+        adj.setdiag(1)                                  # tensormain.py:172
     n, m = adj.shape
     diags = np.asarray(adj.sum(axis=1)).flatten()       # :174
     with np.errstate(divide="ignore"):
@@ -54,9 +56,10 @@ def build_ahat(adj, dtype="float32"):
 
 
 def _softmax_rows(x):
-    x = x - x.max(axis=1, keepdims=True)
-    e = np.exp(x, dtype=F32)
-    return (e / e.sum(axis=1, keepdims=True, dtype=F32)).astype(F32)
+    e = x - x.max(axis=1, keepdims=True)
+    np.exp(e, out=e)
+    e /= e.sum(axis=1, keepdims=True, dtype=F32)
+    return e
 
 
 def _sigmoid(x):
@@ -216,19 +219,32 @@ class GCNOracle:
         return F32(tot)
 
     # ---- forward ---------------------------------------------------------- #
-    def forward(self, params, idx):
+    def forward(self, params, idx, lean=False):
+        """Temporaries are released / reused in place where that does not change a single rounding: at
+        Twitter-World size every [N, F] float32 array is 3.4-5.7 GB and the epoch must fit the host."""
         layers = self.unpack(params)
-        A, act = self.A, _act(self.act)
+        A, act = self.A, self.act
         c = {"layers": layers}
+
+        def activate(p):                                                 # in place; p is not needed afterwards
+            if act == "rectify":
+                return np.maximum(p, F32(0), out=p)
+            if act == "tanh":
+                return np.tanh(p, out=p)
+            return p
         z = np.asarray(self.X @ layers[0]["W"], dtype=F32)               # lasagne_layers.py:65
-        p = np.asarray(A @ z, dtype=F32) + layers[0]["b"][None, :]       # :67-70
-        h = act(p)                                                       # :71
-        c["Z1"], c["A"] = z, [h]
+        p = np.asarray(A @ z, dtype=F32)                                 # :67
+        p += layers[0]["b"][None, :]                                     # :69-70
+        h = activate(p)                                                  # :71
+        c["Z1"], c["A"] = (None if lean else z), [h]
+        del z
         c["Hc"], c["g"] = [None], [None]
         for ly in layers[1:-1]:
-            z = np.dot(h, ly["W"]).astype(F32)                           # :82
-            p = np.asarray(A @ z, dtype=F32) + ly["b"][None, :]          # :84-87
-            hc = act(p)
+            z = np.asarray(np.dot(h, ly["W"]), dtype=F32)                # :82
+            p = np.asarray(A @ z, dtype=F32)                             # :84
+            del z
+            p += ly["b"][None, :]                                        # :86-87
+            hc = activate(p)
             if self.highway:
                 out, g = highway_mix(h, hc, ly["Wg"], ly["bg"])
             else:
@@ -238,9 +254,12 @@ class GCNOracle:
             c["A"].append(out)
             h = out
         ly = layers[-1]
-        z = np.dot(h, ly["W"]).astype(F32)                               # :82
-        p = np.asarray(A @ z, dtype=F32) + ly["b"][None, :]              # :84-87
+        z = np.asarray(np.dot(h, ly["W"]), dtype=F32)                    # :82
+        p = np.asarray(A @ z, dtype=F32)                                 # :84
+        del z
+        p += ly["b"][None, :]                                            # :86-87
         logits = p[idx, :]                                               # :88
+        del p
         c["logits"] = logits
         c["probs"] = _softmax_rows(logits)                               # :89, mlpconv.py:216
         return c
@@ -256,7 +275,10 @@ class GCNOracle:
         c = cache or self.forward(params, idx)
         lg = c["logits"]
         m = lg.max(axis=1, keepdims=True)
-        lse = (m[:, 0] + np.log(np.exp(lg - m, dtype=F32).sum(axis=1, dtype=F32))).astype(F32)
+        e = lg - m
+        np.exp(e, out=e)
+        lse = (m[:, 0] + np.log(e.sum(axis=1, dtype=F32))).astype(F32)
+        del e
         ce = (lse - lg[np.arange(len(y)), y]).astype(F32)
         loss = F32(ce.mean(dtype=F32)) + self.reg_loss(c["layers"])
         acc = float(np.mean(c["probs"].argmax(-1) == y))
@@ -267,12 +289,16 @@ class GCNOracle:
         layers, A = cache["layers"], self.A
         n_idx = len(idx)
         N = A.shape[0]
-        G = cache["probs"].copy()
+        G = cache["probs"] if cache.get("keep", None) == () else cache["probs"].copy()   # lean: reuse the buffer
         G[np.arange(n_idx), y] -= F32(1)
-        G = (G / F32(n_idx)).astype(F32)
+        G /= F32(n_idx)
         C = G.shape[1]
         dP = np.zeros((N, C), F32)
-        np.add.at(dP, idx, G)                    # scatter-ADD: duplicates accumulate
+        idx = np.asarray(idx)
+        if len(np.unique(idx)) == n_idx:
+            dP[idx] = G                          # no duplicates: the scatter-add is a placement
+        else:
+            np.add.at(dP, idx, G)                # scatter-ADD: duplicates accumulate
         grads = [None] * len(layers)
         acts = cache["A"]
         # output layer
@@ -280,8 +306,12 @@ class GCNOracle:
         h_in = acts[-1]
         db = dP.sum(axis=0, dtype=F32)
         dZ = np.asarray(A @ dP, dtype=F32)       # A^T = A
+        if "dP_out" not in cache.get("keep", ("dP_out",)):
+            del dP, G
+            cache["probs"] = None
         dW = np.dot(h_in.T, dZ).astype(F32) + F32(0.5) * self.c_out * (np.sign(ly["W"]) + F32(2) * ly["W"])
-        dH = np.dot(dZ, ly["W"].T).astype(F32)
+        dH = np.asarray(np.dot(dZ, ly["W"].T), dtype=F32)
+        del dZ
         grads[-1] = dict(W=dW.astype(F32), b=db)
         # hidden conv layers L-1 .. 2
         for li in range(len(layers) - 2, 0, -1):
@@ -314,7 +344,9 @@ class GCNOracle:
         dW1 = (np.asarray(self.XT @ dZ1, dtype=F32)
                + F32(0.5) * self.c_hid * (np.sign(ly["W"]) + F32(2) * ly["W"])).astype(F32)
         grads[0] = dict(W=dW1, b=db1)
-        cache["dP_out"], cache["dZ1"], cache["dP1"] = dP, dZ1, dP1
+        cache["dZ1"], cache["dP1"] = dZ1, dP1
+        if "dP_out" in cache.get("keep", ("dP_out",)):
+            cache["dP_out"] = dP
         # flatten in parameter order
         flat = []
         for gr in grads:
@@ -323,9 +355,14 @@ class GCNOracle:
                 flat += [gr["Wg"], gr["bg"]]
         return flat
 
-    def loss_and_grads(self, params, idx, y):
-        c = self.forward(params, idx)
+    def loss_and_grads(self, params, idx, y, lean=False):
+        """``lean``: drop the intermediates only tests look at (memory at Twitter-World size)."""
+        c = self.forward(params, idx, lean=lean)
+        if lean:
+            c["keep"] = ()
         loss, acc = self.loss_acc(params, idx, y, cache=c)
+        if lean:
+            c["logits"] = None
         return loss, acc, self.backward(c, idx, y), c
 
 

@@ -1,0 +1,85 @@
+"""Parity of one training step AT THE BENCHED SIZES (BASELINE configs 3 and 4) with the bench's own settings
+(auto GEMM engine -> tcgen05 3xTF32, propagate-first output layer, document-blocked X^T.dZ1, nodes reordered by
+region): every operation of f_train compared with the oracle on sampled rows (oracle/sampled_parity.py).
+Bound: |gpu - oracle| <= 1e-6 + 1e-4*|oracle| (north_star), reported as max scaled error <= 1."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from oracle import sampled_parity  # noqa: E402
+
+
+def build(name, n_layers=3, highway=True, **kw):
+    from graphconvgeo_b200 import synth
+    from graphconvgeo_b200.mlpconv import MLPCONV
+    big = name in ("twitter-us", "twitter-world")
+    wl = synth.make_workload_device(name, device="cuda", seed=77) if big else synth.make_workload(name)
+    m = MLPCONV(n_epochs=1, regul_coefs=[1e-6, 1e-6], hidden_layer_size=wl.hidden, drop_out=False, n_layers=n_layers,
+                highway=highway, seed=1, cuda_graph=False, **kw)
+    m.prepare(wl.X, wl.train_indices, wl.dev_indices, wl.test_indices, wl.Y, wl.A_hat)
+    return m, wl
+
+
+def run_check(m, steps_before=2, **kw):
+    for _ in range(steps_before):          # Adam state and parameters away from their initial values
+        m.f_train()
+    Xh, Ah = m.host_inputs()
+    lines = []
+    rep = sampled_parity.check_training_step(m, Xh, Ah, log=lines.append, **kw)
+    return rep, lines
+
+
+@pytest.mark.parametrize("n_layers,highway", [(2, False), (3, True)])
+def test_small_model_every_operation_within_tolerance(n_layers, highway):
+    m, wl = build("tiny", n_layers, highway)
+    rep, lines = run_check(m, n_rows=400, n_param_rows=16)
+    assert rep["n_checks"] >= (14 if n_layers == 2 else 28)
+    assert rep["max_scaled_err"] <= 1.0, "\n".join(lines)
+
+
+def test_checker_detects_a_wrong_gradient(monkeypatch):
+    """The check is not vacuous: a bias gradient that is off by 0.1 % is reported far over tolerance."""
+    from graphconvgeo_b200 import ops
+    m, wl = build("tiny", 3, True)
+    orig = ops.colsum
+
+    def bad_colsum(X, out=None):
+        r = orig(X, out=out)
+        r.mul_(1.001)
+        return r
+    monkeypatch.setattr(ops, "colsum", bad_colsum)
+    rep, lines = run_check(m, steps_before=0, n_rows=300, n_param_rows=8)
+    assert rep["max_scaled_err"] > 5.0
+    assert "colsum" in rep["worst_check"] or "adam" in rep["worst_check"] or "db" in rep["worst_check"]
+
+
+def test_duplicate_target_indices_scatter_add_is_checked():
+    """tensormain.py:226 samples train indices WITH replacement: the scatter-add of the backward sums duplicates."""
+    from graphconvgeo_b200 import synth
+    from graphconvgeo_b200.mlpconv import MLPCONV
+    wl = synth.make_workload("tiny")
+    rng = np.random.RandomState(4)
+    idx = rng.choice(len(wl.train_indices), size=len(wl.train_indices), replace=True).astype(np.int32)
+    m = MLPCONV(n_epochs=1, regul_coefs=[1e-6, 1e-6], hidden_layer_size=wl.hidden, n_layers=3, highway=True, seed=1,
+                cuda_graph=False)
+    m.prepare(wl.X, idx, wl.dev_indices, wl.test_indices, wl.Y, wl.A_hat)
+    m.l_out.propagate_first = True
+    rep, lines = run_check(m, n_rows=300, n_param_rows=8)
+    assert any("scatter-add" in k for k in rep["checks"])
+    assert rep["max_scaled_err"] <= 1.0, "\n".join(lines)
+
+
+@pytest.mark.parametrize("name", ["twitter-us", "twitter-world"])
+def test_benched_configuration_every_operation_within_tolerance(name):
+    """BASELINE configs 3 / 4 with the bench's settings: tcgen05 3xTF32 GEMMs, region reordering, blocked X^T.dZ1,
+    propagate-first output layer where it widens (Twitter-World: 600 -> 1024)."""
+    from graphconvgeo_b200 import ops
+    m, wl = build(name)
+    assert m.node_order is not None                                   # reorder="auto" -> labels at this size
+    assert ops.gemm_uses_tensor_cores(wl.X.shape[0], wl.hidden, wl.hidden)
+    assert m.l_out.propagate_first == (wl.n_classes > wl.hidden)
+    rep, lines = run_check(m, steps_before=2, n_rows=1024, n_param_rows=16)
+    print("\n".join(lines))
+    assert rep["max_scaled_err"] <= 1.0, "\n".join(l for l in lines if "scaled" in l)

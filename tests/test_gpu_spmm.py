@@ -21,9 +21,9 @@ def run_spmm(A, B, thr=256, **kw):
 
 
 @pytest.mark.parametrize("F", [1, 3, 4, 16, 20, 64, 76, 100, 128, 256, 300, 600, 930, 1024])
-@pytest.mark.parametrize("panel", [-1, 0, 16, 64])
+@pytest.mark.parametrize("panel", [-2, -1, 0, 16, 64])
 def test_bit_exact_vs_scipy(F, panel):
-    rng = np.random.RandomState(F + panel)
+    rng = np.random.RandomState(F + panel + 2)
     A = random_csr(rng, 700, 500, 9)
     B = rng.standard_normal((500, F)).astype(np.float32)
     got, _ = run_spmm(A, B, thr=10 ** 6, panel_cols=panel)
@@ -31,7 +31,7 @@ def test_bit_exact_vs_scipy(F, panel):
     assert np.array_equal(got, ref), "max diff %g" % np.abs(got - ref).max()
 
 
-@pytest.mark.parametrize("panel", [-1, 0, 16, 32, 128, 512])
+@pytest.mark.parametrize("panel", [-2, -1, 0, 16, 32, 128, 512])
 def test_hub_rows_are_split_deterministically(panel):
     rng = np.random.RandomState(1)
     A = random_csr(rng, 400, 5000, 6, hub_rows=(0, 17, 399), hub_deg=3000)
@@ -98,6 +98,79 @@ def test_fused_highway_gate_epilogue():
     assert np.array_equal(got, got3)            # bulk-copy staged variant: same bits
 
 
+STREAM_F = [4, 100, 128, 200, 256, 300, 384, 500, 600, 700, 1024]      # 1, 2, 3, 4, 5, 8 float4 per lane
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6, 7, 8])
+def test_streaming_variants_are_bit_exact(variant):
+    """Every kernel of gcg_spmm_stream.cu (shared-memory ring depths, register pipelines), short spans so that
+    span / chunk / row boundaries fall everywhere, hub rows split into segments, empty rows, epilogues."""
+    from graphconvgeo_b200 import _lib, ops
+    from graphconvgeo_b200.sparse import CSRMatrix
+    rng = np.random.RandomState(100 + variant)
+    A = random_csr(rng, 900, 700, 11, hub_rows=(3, 450, 899), hub_deg=650, empty_frac=0.2)
+    Ad = CSRMatrix.from_scipy(A, "cuda", long_row_threshold=64)
+    L = _lib.lib()
+    try:
+        for span in (32, 100, 384):
+            L.gcg_spmm_stream_tuning(variant, span)
+            for F in STREAM_F:
+                B = rng.standard_normal((700, F)).astype(np.float32)
+                b = rng.standard_normal(F).astype(np.float32)
+                got = ops.spmm(Ad, to_dev(B), bias=to_dev(b), act="rectify", panel_cols=-2).cpu().numpy()
+                want = ops.spmm(Ad, to_dev(B), bias=to_dev(b), act="rectify", panel_cols=0).cpu().numpy()
+                assert np.array_equal(got, want), (variant, span, F)     # same bits as the register-gather kernel
+                ref = np.maximum(np.asarray(A @ B, dtype=np.float32) + b[None, :], 0)
+                short = np.diff(A.indptr) <= 64
+                assert np.array_equal(got[short], ref[short]), (variant, span, F)   # and as scipy, unsplit rows
+    finally:
+        L.gcg_spmm_stream_tuning(0, 0)
+
+
+@pytest.mark.parametrize("sched", [([0, 1000], [3]), ([0, 1000], [-5]), ([0, 10, 10, 400, 1000], [1, 4, -2, 6]),
+                                   ([0, 999, 1000], [64, 2])])
+def test_streaming_block_panel_schedules_are_bit_exact(sched):
+    from graphconvgeo_b200 import _lib, ops
+    from graphconvgeo_b200.sparse import CSRMatrix
+    rng = np.random.RandomState(7)
+    A = random_csr(rng, 1000, 800, 9, hub_rows=(0, 500), hub_deg=700)
+    Ad = CSRMatrix.from_scipy(A, "cuda", long_row_threshold=128)
+    _lib.lib().gcg_spmm_stream_tuning(0, 64)
+    try:
+        for F in (24, 300, 600, 930):
+            B = to_dev(rng.standard_normal((800, F)).astype(np.float32))
+            want = ops.spmm(Ad, B, panel_cols=0)
+            Ad.set_schedule(None)
+            assert torch.equal(ops.spmm(Ad, B, panel_cols=-2), want)
+            Ad.set_schedule(*sched)
+            assert torch.equal(ops.spmm(Ad, B, panel_cols=-2), want), (sched, F)
+    finally:
+        _lib.lib().gcg_spmm_stream_tuning(0, 0)
+    with pytest.raises(_lib.GcgError):
+        Ad.set_schedule([0, 500], [1])                       # does not cover all rows
+
+
+def test_streaming_gate_accumulate_and_row_slices():
+    from graphconvgeo_b200 import ops
+    from graphconvgeo_b200.sparse import CSRMatrix
+    rng = np.random.RandomState(9)
+    n, F = 333, 300
+    A = random_csr(rng, n, n, 8, hub_rows=(5,), hub_deg=300)
+    Ad = CSRMatrix.from_scipy(A, "cuda", long_row_threshold=64)
+    B = to_dev((rng.standard_normal((n, F)) * 0.2).astype(np.float32))
+    b = to_dev((rng.standard_normal(F) * 0.1).astype(np.float32))
+    g, h = to_dev(rng.rand(n, F).astype(np.float32)), to_dev(rng.standard_normal((n, F)).astype(np.float32))
+    c0, c2 = ops.alloc_mat(n, F, "cuda"), ops.alloc_mat(n, F, "cuda")
+    want = ops.spmm(Ad, B, bias=b, act="tanh", gate=g, carry=h, conv_out=c0, panel_cols=0)
+    got = ops.spmm(Ad, B, bias=b, act="tanh", gate=g, carry=h, conv_out=c2, panel_cols=-2)
+    assert torch.equal(got, want) and torch.equal(c0, c2)
+    acc0 = ops.spmm(Ad, B, panel_cols=0)
+    acc2 = acc0.clone()
+    ops.spmm(Ad, B, out=acc0, accumulate=True, act="rectify", panel_cols=0)
+    ops.spmm(Ad, B, out=acc2, accumulate=True, act="rectify", panel_cols=-2)
+    assert torch.equal(acc0, acc2)
+
+
 def test_accumulate_mode():
     rng = np.random.RandomState(5)
     A1, A2 = random_csr(rng, 200, 150, 5), random_csr(rng, 200, 150, 5)
@@ -160,7 +233,7 @@ def test_property_random_shapes():
 
     @settings(max_examples=25, deadline=None)
     @given(st.integers(1, 300), st.integers(1, 300), st.integers(1, 160), st.integers(0, 12),
-           st.sampled_from([-1, 0, 16, 32, 64]), st.integers(0, 2 ** 31 - 1))
+           st.sampled_from([-2, -1, 0, 16, 32, 64]), st.integers(0, 2 ** 31 - 1))
     def prop(n, k, F, deg, panel, seed):
         rng = np.random.RandomState(seed)
         A = random_csr(rng, n, k, deg, hub_rows=(0,), hub_deg=min(k, 70))
@@ -201,6 +274,10 @@ def test_full_size_properties_twitter_world_shape():
     # panel-major execution and the bulk-copy staged kernel give the same bits as whole-row execution
     assert torch.equal(ops.spmm(Ad, x, panel_cols=16), ax)
     assert torch.equal(ops.spmm(Ad, x, panel_cols=-1), ops.spmm(Ad, x, panel_cols=0))
+    # so does the nnz-balanced streaming kernel, whole rows and under a block x panel schedule
+    assert torch.equal(ops.spmm(Ad, x, panel_cols=-2), ax)
+    Ad.set_schedule([0, 300_000, 300_000, 1_000_001, n], [2, 1, -2, 1])
+    assert torch.equal(ops.spmm(Ad, x, panel_cols=-2), ax)
 
 
 def test_document_blocked_transpose_product_matches_plain():
