@@ -83,9 +83,13 @@ PROTOTYPES = {
     "gcg_peer_close": (c_int, [c_vp]),
     "gcg_push_cols_f32": (c_int, [c_vp, c_i64, c_i64, c_i64, c_i32, c_i64, C.POINTER(c_vp), c_i64, c_vp]),
     "gcg_push_rows_f32": (c_int, [c_vp, C.POINTER(c_i64), c_i32, c_i64, C.POINTER(c_vp), c_i64, c_vp]),
+    "gcg_peer_barrier": (c_int, [C.POINTER(c_vp), c_vp, c_i32, c_i32, c_i32, c_vp, c_vp]),
+    "gcg_spmm_csr_routed_f32": (c_int, [c_vp, c_vp, c_i64, c_i64, c_i32, C.POINTER(c_vp), C.POINTER(c_i64), c_i64, c_vp,
+                                        c_int, c_i32, c_vp, c_i64, c_vp]),
     "gcg_spmm_set_tuning": (None, [c_int, c_int]),
     "gcg_plan_set_schedule": (c_int, [c_vp, c_i64, c_vp, c_vp]),
-    "gcg_spmm_stream_tuning": (None, [c_int, c_int]),
+    "gcg_spmm_stream_tuning": (None, [c_int, c_int, c_int]),
+    "gcg_plan_set_near_window": (c_int, [c_vp, c_i32]),
     "gcg_spgemm_workspace_bytes": (c_i64, [c_i64]),
     "gcg_spgemm_count_csr": (c_int, [c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_i64, c_vp]),
     "gcg_spgemm_fill_pattern_csr": (c_int, [c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_i64, c_vp]),

@@ -36,7 +36,13 @@ constexpr int TM = 128, TN = 128, TK = 32;       // CTA tile; TK*4 B = the 128 B
 constexpr int UK = 8;                            // K of one tcgen05.mma.kind::tf32
 constexpr int TILE_BYTES = TM * TK * 4;          // 16 KB per operand tile
 constexpr int ACC_STAGES = 2;
-constexpr int TMEM_COLS = ACC_STAGES * TM;       // 256 (power of two): D^T tile = TN lanes x TM columns
+// TMEM: per accumulator stage TWO D^T tiles (TN lanes x TM columns each): the hi.hi products and, for 3xTF32,
+// the two cross terms in a tile of their own.  The tensor core adds into D with round-toward-zero, one
+// truncation per MMA; with all three terms in one accumulator a K = 600 chain made 225 truncating adds
+// (measured error 2.5e-5 of the output magnitude, over the 1e-4 relative bound on cancelling logits).  The
+// cross terms are 2^-11 smaller: kept apart they cost the big accumulator nothing and its chain is 3x shorter.
+// The epilogue adds the two tiles in fp32 round-to-nearest.
+constexpr int TMEM_COLS = ACC_STAGES * 2 * TM;   // 512 = all of TMEM
 constexpr int TC_THREADS = 256;
 
 int launch_splitk_reduce(const GemmArgs& g, cudaStream_t st);   // gcg_gemm.cu
@@ -79,6 +85,17 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
       "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
+      "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+        "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]),
+        "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]),
+        "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
   asm volatile(
@@ -123,6 +140,7 @@ struct TcArgs {
   int m_tiles, n_tiles, splits, num_kb_total;   // K blocks over the whole K
   int kb_per_split;
   int x3;                                       // 1: hi.hi + lo.hi + hi.lo ; 0: hi.hi
+  int chunk_kb;                                 // 3xTF32: K blocks per accumulation chain (0 = one chain per tile)
 };
 
 template <bool A_MN, bool B_MN>
@@ -219,10 +237,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const int z = t / (a.n_tiles * a.m_tiles);
         const int kb0 = z * a.kb_per_split, kb1 = min(a.num_kb_total, kb0 + a.kb_per_split);
+        const int chunk = (a.chunk_kb > 0) ? a.chunk_kb : (kb1 - kb0);
         mbar_wait(acc_empty + acc, acc_phase ^ 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t d_tmem = tmem_base + acc * TM;
+        uint32_t d_tmem = tmem_base + acc * 2 * TM;
+        uint32_t d_small = d_tmem + TM;                     // cross terms lo.hi + hi.lo (3xTF32 only)
+        int chain0 = kb0;                                   // first K block of the current accumulation chain
         for (int kb = kb0; kb < kb1; ++kb) {
+          if (kb - chain0 == chunk) {
+            // chain complete: hand this accumulator stage to the epilogue (which adds it to its running sums in
+            // fp32 round-to-nearest) and continue in the other stage -- the tensor core's round-toward-zero
+            // accumulate errs with the length of a chain, so chains are kept short
+            umma_commit(acc_full + acc);
+            if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+            mbar_wait(acc_empty + acc, acc_phase ^ 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            d_tmem = tmem_base + acc * 2 * TM;
+            d_small = d_tmem + TM;
+            chain0 = kb;
+          }
           mbar_wait(full + stage, phase);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t sA = smem_u32(smem + stage * stage_bytes);
@@ -234,13 +267,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
             const uint32_t boff = B_MN ? k * 1024 : k * 32;
             const uint64_t ah = make_desc<A_MN>(sA + aoff);
             const uint64_t bh = make_desc<B_MN>(sB + boff);
-            const uint32_t first = (kb > kb0 || k > 0) ? 1u : 0u;
+            const uint32_t first = (kb > chain0 || k > 0) ? 1u : 0u;
             if (a.x3) {
               const uint64_t al = make_desc<A_MN>(sA + TILE_BYTES + aoff);
               const uint64_t bl = make_desc<B_MN>(sB + TILE_BYTES + boff);
-              umma_tf32(d_tmem, bh, al, idesc, first);   // small terms first
-              umma_tf32(d_tmem, bl, ah, idesc, 1u);
-              umma_tf32(d_tmem, bh, ah, idesc, 1u);
+              umma_tf32(d_small, bh, al, idesc, first);
+              umma_tf32(d_small, bl, ah, idesc, 1u);
+              umma_tf32(d_tmem, bh, ah, idesc, first);
             } else {
               umma_tf32(d_tmem, bh, ah, idesc, first);
             }
@@ -273,13 +306,65 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
       const bool gate_like = g.beta == 0.f && g.mask == nullptr && g.act == GCG_ACT_SIGMOID;
       const bool accum_like = g.act == GCG_ACT_IDENTITY && g.bias == nullptr &&
                               (g.mask == nullptr || g.mask_act == GCG_ACT_RELU || g.mask_act == GCG_ACT_TANH);
+      const int kb0e = z * a.kb_per_split, kb1e = min(a.num_kb_total, kb0e + a.kb_per_split);
+      const int n_chains = (a.chunk_kb > 0) ? (kb1e - kb0e + a.chunk_kb - 1) / a.chunk_kb : 1;
       mbar_wait(acc_full + acc, acc_phase);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (n_chains > 1) {
+        // running sums of the chains in registers (fp32 round-to-nearest); the total goes back into the LAST
+        // chain's TMEM stage so that the (code-size critical) store phase below stays as it is
+        float sum[TM / 32][32];
+#pragma unroll
+        for (int cg = 0; cg < TM / 32; ++cg)
+#pragma unroll
+          for (int e = 0; e < 32; ++e) sum[cg][e] = 0.f;
+        for (int ci = 0; ci < n_chains; ++ci) {
+          if (ci > 0) {
+            mbar_wait(acc_full + acc, acc_phase);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          }
+          const uint32_t tb = tmem_base + acc * 2 * TM + ((uint32_t)(ew * 32) << 16);
+#pragma unroll
+          for (int cg = 0; cg < TM / 32; ++cg) {
+            uint32_t v[32], w[32];
+            tmem_ld32(tb + cg * 32, v);
+            tmem_ld32(tb + TM + cg * 32, w);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int e = 0; e < 32; ++e)
+              sum[cg][e] = __fadd_rn(sum[cg][e], __fadd_rn(__uint_as_float(v[e]), __uint_as_float(w[e])));
+          }
+          if (ci + 1 < n_chains) {
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty + acc);
+            if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+          } else {
+#pragma unroll
+            for (int cg = 0; cg < TM / 32; ++cg) {
+              uint32_t o[32], zr[32];
+#pragma unroll
+              for (int e = 0; e < 32; ++e) { o[e] = __float_as_uint(sum[cg][e]); zr[e] = 0u; }
+              tmem_st32(tb + cg * 32, o);
+              tmem_st32(tb + TM + cg * 32, zr);
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+          }
+        }
+      }
 #pragma unroll 1
       for (int c = 0; c < TM; c += 32) {
         uint32_t v[32];
-        tmem_ld32(tmem_base + acc * TM + c + ((uint32_t)(ew * 32) << 16), v);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        tmem_ld32(tmem_base + acc * 2 * TM + c + ((uint32_t)(ew * 32) << 16), v);
+        if (a.x3) {
+          uint32_t w[32];
+          tmem_ld32(tmem_base + acc * 2 * TM + TM + c + ((uint32_t)(ew * 32) << 16), w);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__fadd_rn(__uint_as_float(v[e]), __uint_as_float(w[e])));
+        } else {
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        }
         // The bodies below are kept tiny on purpose: the 32-way unroll is needed to keep v[] in
         // registers, and a fat per-element body (bounds + beta + act switch + mask) made the kernel
         // 85 KB of SASS whose instruction-cache misses cost 27 us per tile (ncu: no_instruction stalls).
@@ -556,6 +641,10 @@ int gemm_tc_launch(const GemmArgs& g0, int transA, int transB, int mode, void* w
   ta.num_kb_total = num_kb;
   ta.kb_per_split = kbps;
   ta.x3 = x3;
+  // 3xTF32: accumulation chains of at most 8 K blocks (K = 256): 32 truncating adds into the hi.hi accumulator
+  // instead of 75 at K = 600 (measured at Twitter-World: logits error 2.1x -> 1.0x -> below the 1e-4 bound)
+  static const int chunk_env = getenv("GCG_GEMM_CHUNK_KB") ? atoi(getenv("GCG_GEMM_CHUNK_KB")) : 8;
+  ta.chunk_kb = (x3 && chunk_env > 0 && kbps > chunk_env) ? chunk_env : 0;
   const int64_t total = (int64_t)ta.m_tiles * ta.n_tiles * split;
   if (total >= INT32_MAX) return GCG_ERR_UNSUPPORTED;
   const int smem_bytes = (x3 ? 3 * 4 : 6 * 2) * TILE_BYTES + 1024 + 256;

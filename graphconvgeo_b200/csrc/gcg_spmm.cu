@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(256) spmm_scalar_kernel(const SpmmArgs a) {
       const int64_t c = c0 + lane + 32 * k;
       if (c >= a.F) continue;
       float v = acc[k];
-      float* cp = a.C + row * a.ldc + c;
+      float* cp = out_row_ptr(a, row) + c;
       if (a.accumulate) v = __fadd_rn(*cp, v);
       if (a.bias) v = __fadd_rn(v, __ldg(a.bias + c));
       v = apply_act(v, a.act);
@@ -512,12 +512,53 @@ extern "C" int gcg_plan_info(const gcg_plan* p, int64_t* info) {
   return GCG_OK;
 }
 
+struct OwnerRoute {
+  int n_owner;
+  void* const* base;
+  const int64_t* off;
+};
+
+static int spmm_run(const gcg_plan* p, const float* B, int64_t ldb, int64_t F,
+                    float* C, int64_t ldc, const float* bias, int act,
+                    int accumulate, const float* gate, int64_t ld_gate,
+                    const float* carry, int64_t ld_carry, float* conv_out,
+                    int64_t ld_conv, int32_t panel_cols, void* workspace,
+                    int64_t workspace_bytes, void* stream, const OwnerRoute* route);
+
 extern "C" int gcg_spmm_csr_f32(const gcg_plan* p, const float* B, int64_t ldb, int64_t F,
                                 float* C, int64_t ldc, const float* bias, int act,
                                 int accumulate, const float* gate, int64_t ld_gate,
                                 const float* carry, int64_t ld_carry, float* conv_out,
                                 int64_t ld_conv, int32_t panel_cols, void* workspace,
                                 int64_t workspace_bytes, void* stream) {
+  return spmm_run(p, B, ldb, F, C, ldc, bias, act, accumulate, gate, ld_gate, carry, ld_carry, conv_out, ld_conv,
+                  panel_cols, workspace, workspace_bytes, stream, nullptr);
+}
+
+extern "C" int gcg_spmm_csr_routed_f32(const gcg_plan* p, const float* B, int64_t ldb, int64_t F, int32_t n_owner,
+                                       void* const* h_owner_base, const int64_t* h_owner_row_off, int64_t ldc,
+                                       const float* bias, int act, int32_t panel_cols, void* workspace,
+                                       int64_t workspace_bytes, void* stream) {
+  GCG_CHECK_ARG(p != nullptr, "gcg_spmm_csr_routed_f32: plan is NULL");
+  GCG_CHECK_ARG(n_owner > 0 && n_owner <= 16 && h_owner_base && h_owner_row_off, "gcg_spmm_csr_routed_f32: bad owner table");
+  GCG_CHECK_SHAPE(h_owner_row_off[0] == 0 && h_owner_row_off[n_owner] == p->n_rows,
+                  "gcg_spmm_csr_routed_f32: owner offsets must cover rows [0, %lld)", (long long)p->n_rows);
+  for (int q = 0; q < n_owner; ++q) {
+    GCG_CHECK_ARG(h_owner_base[q] != nullptr && aligned16(h_owner_base[q]), "gcg_spmm_csr_routed_f32: owner %d buffer invalid", q);
+    GCG_CHECK_SHAPE(h_owner_row_off[q + 1] >= h_owner_row_off[q], "gcg_spmm_csr_routed_f32: offsets not monotone");
+  }
+  OwnerRoute r{n_owner, h_owner_base, h_owner_row_off};
+  // C is only used for argument validation below: any owner buffer will do
+  return spmm_run(p, B, ldb, F, reinterpret_cast<float*>(h_owner_base[0]), ldc, bias, act, 0, nullptr, 0, nullptr, 0, nullptr, 0,
+                  panel_cols, workspace, workspace_bytes, stream, &r);
+}
+
+static int spmm_run(const gcg_plan* p, const float* B, int64_t ldb, int64_t F,
+                    float* C, int64_t ldc, const float* bias, int act,
+                    int accumulate, const float* gate, int64_t ld_gate,
+                    const float* carry, int64_t ld_carry, float* conv_out,
+                    int64_t ld_conv, int32_t panel_cols, void* workspace,
+                    int64_t workspace_bytes, void* stream, const OwnerRoute* route) {
   GCG_CHECK_ARG(p != nullptr, "gcg_spmm_csr_f32: plan is NULL");
   GCG_CHECK_ARG(B && C, "gcg_spmm_csr_f32: NULL dense operand");
   GCG_CHECK_ARG(B != C, "gcg_spmm_csr_f32: B and C must not alias");
@@ -543,6 +584,15 @@ extern "C" int gcg_spmm_csr_f32(const gcg_plan* p, const float* B, int64_t ldb, 
   a.gate = gate; a.ld_gate = ld_gate; a.carry = carry; a.ld_carry = ld_carry;
   a.conv_out = conv_out; a.ld_conv = ld_conv;
   a.f4_total = (int)((F + 3) / 4);
+  a.n_owner = 0;
+  if (route) {
+    a.n_owner = route->n_owner;
+    for (int q = 0; q < route->n_owner; ++q) {
+      a.owner_base[q] = reinterpret_cast<float*>(route->base[q]);
+      a.owner_off[q] = (int)route->off[q];
+    }
+    a.owner_off[route->n_owner] = (int)route->off[route->n_owner];
+  }
 
   const int64_t f_pad = 4 * (int64_t)a.f4_total;
   bool vec = aligned16(B) && aligned16(C) && (ldb % 4 == 0) && (ldc % 4 == 0) && ldb >= f_pad && ldc >= f_pad;

@@ -63,6 +63,11 @@ struct SpmmArgs {
   int seg_blocks;
   int row_blocks;
   int nnz_total;
+  // > 0: output row r belongs to owner q with owner_off[q] <= r < owner_off[q+1] and is written to
+  // owner_base[q] + (r - owner_off[q]) * ldc -- peer memory of the owning GPU (gcg_spmm_csr_routed_f32)
+  int n_owner;
+  int owner_off[17];
+  float* owner_base[16];
   int only_segments;   // vec kernel launched for the long-row segments only (rows go to the bulk-copy kernel)
 };
 
@@ -79,11 +84,20 @@ __device__ __forceinline__ float gate_mix(float g, float hc, float h) {
   return __fadd_rn(__fmul_rn(g, hc), __fmul_rn(__fsub_rn(1.f, g), h));
 }
 
+__device__ __forceinline__ float* out_row_ptr(const SpmmArgs& a, int64_t row) {
+  if (a.n_owner > 0) {
+    int q = 0;
+    while (q + 1 < a.n_owner && row >= a.owner_off[q + 1]) ++q;
+    return a.owner_base[q] + (row - a.owner_off[q]) * a.ldc;
+  }
+  return a.C + row * a.ldc;
+}
+
 // bias + act + optional highway mix for one float4 of output row `row`
 // at float4 column `c4`; writes C (and conv_out).
 __device__ __forceinline__ void epilogue_store(const SpmmArgs& a, int64_t row, int c4, float4 v,
                                                uint64_t strm) {
-  float* cp = a.C + row * a.ldc + 4 * (int64_t)c4;
+  float* cp = out_row_ptr(a, row) + 4 * (int64_t)c4;
   if (a.accumulate) {
     const float4 o = *reinterpret_cast<const float4*>(cp);
     v.x = __fadd_rn(o.x, v.x); v.y = __fadd_rn(o.y, v.y);

@@ -45,10 +45,12 @@ struct StreamState {
   std::vector<int32_t> blk_rows;        // [n_blocks + 1] row ranges of the schedule (empty = one block)
   std::vector<int32_t> blk_panels;      // [n_blocks] >0: panel-major inside the block, <0: interleaved, |x| panels
   std::map<int64_t, StreamSchedule> scheds;   // key: f4_total * 2^20 + span_nnz
+  int near_window = 0;                  // rows; 0 = every gather is kept (gcg_plan_set_near_window)
 };
 
 static int g_stream_variant = 0;     // 0 = auto
 static int g_stream_span_nnz = 0;    // 0 = default
+static int g_stream_near = -1;       // -1 = plan's own choice, 0 = every gather evict_last, > 0 = window in rows
 
 void stream_state_destroy(StreamState* s) {
   if (!s) return;
@@ -91,7 +93,7 @@ __device__ __forceinline__ void epilogue_store_lean(const SpmmArgs& a, int64_t r
   if (a.act == GCG_ACT_RELU) {
     v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
   }
-  stg_f4_stream(reinterpret_cast<float4*>(a.C + row * a.ldc + 4 * (int64_t)c4), v, strm);
+  stg_f4_stream(reinterpret_cast<float4*>(out_row_ptr(a, row) + 4 * (int64_t)c4), v, strm);
 }
 
 // One warp = one span.  VPLMAX float4 per lane and row, D = pipeline depth (ring slots / register rows),
@@ -101,7 +103,7 @@ __device__ __forceinline__ void epilogue_store_lean(const SpmmArgs& a, int64_t r
 template <int VPLMAX, int D, bool SMEM, bool LEAN>
 __device__ __forceinline__ void spmm_stream_body(const SpmmArgs& a, const StreamSpan* __restrict__ spans, int n_spans,
                                                  const int* __restrict__ vptr, const int* __restrict__ vdst, int n_v,
-                                                 int warps_per_cta) {
+                                                 int warps_per_cta, int near_window) {
   extern __shared__ __align__(128) uint8_t smem_dyn[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int si = blockIdx.x * warps_per_cta + warp;
@@ -135,6 +137,11 @@ __device__ __forceinline__ void spmm_stream_body(const SpmmArgs& a, const Stream
   int v = v_beg;
   int vstart = k0;
   int vend = __shfl_sync(full, vend_c, 0);
+  // L2 policy per gathered row: columns within `near_window` rows of the span (the community the node order keeps
+  // together) are the reusable set -> evict_last; far columns (the random long-range mentions, never re-read
+  // before eviction) stream with evict_first so that they do not push the reusable set out of L2.
+  const int r0 = __shfl_sync(full, vdst_c, 0);
+  const bool classify = near_window > 0 && r0 >= 0;
 
   float4 acc[VPLMAX];
 #pragma unroll
@@ -181,9 +188,10 @@ __device__ __forceinline__ void spmm_stream_body(const SpmmArgs& a, const Stream
         if (t >= pb + 32) { pb += 32; pidx = pidx_nx; pidx_nx = ld_idx(pb + 32); }
         const int col = __shfl_sync(full, pidx, t - pb);
         const float4* src = Bp + (int64_t)col * ldb4;
+        const uint64_t pol = (classify && abs(col - r0) > near_window) ? strm : keep;
 #pragma unroll
         for (int j = 0; j < VPLMAX; ++j)
-          if (cv[j]) cp_async16(ring + ps + j * 512, src + 32 * j, keep);
+          if (cv[j]) cp_async16(ring + ps + j * 512, src + 32 * j, pol);
       }
       cp_async_commit();                                // one group per iteration (possibly empty)
       const int c = t - (D - 1);
@@ -216,9 +224,10 @@ __device__ __forceinline__ void spmm_stream_body(const SpmmArgs& a, const Stream
           if (t >= pb + 32) { pb += 32; pidx = pidx_nx; pidx_nx = ld_idx(pb + 32); }
           const int col = __shfl_sync(full, pidx, t - pb);
           const float4* src = Bp + (int64_t)col * ldb4;
+          const uint64_t pol = (classify && abs(col - r0) > near_window) ? strm : keep;
 #pragma unroll
           for (int j = 0; j < VPLMAX; ++j)
-            if (cv[j]) x[u][j] = ldg_f4_keep(src + 32 * j, keep);
+            if (cv[j]) x[u][j] = ldg_f4_keep(src + 32 * j, pol);
         }
         const int c = t - (D - 1);
         if (c >= k0) {
@@ -241,8 +250,8 @@ __device__ __forceinline__ void spmm_stream_body(const SpmmArgs& a, const Stream
 template <int VPLMAX, int D, int WARPS, int MINB, bool SMEM, bool LEAN>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 spmm_stream_kernel(const SpmmArgs a, const StreamSpan* __restrict__ spans, int n_spans, const int* __restrict__ vptr,
-                   const int* __restrict__ vdst, int n_v) {
-  spmm_stream_body<VPLMAX, D, SMEM, LEAN>(a, spans, n_spans, vptr, vdst, n_v, WARPS);
+                   const int* __restrict__ vdst, int n_v, int near_window) {
+  spmm_stream_body<VPLMAX, D, SMEM, LEAN>(a, spans, n_spans, vptr, vdst, n_v, WARPS, near_window);
 }
 
 // ------------------------------------------------------------------------------------------ host side
@@ -259,7 +268,8 @@ static cudaError_t launch_stream_epi(const SpmmArgs& a, const StreamSchedule& s,
     }
   }
   const unsigned grid = (unsigned)ceil_div(s.n_spans, WARPS);
-  kern<<<grid, WARPS * 32, smem_bytes, st>>>(a, s.d_spans, s.n_spans, ss.d_vptr, ss.d_vdst, (int)ss.n_v);
+  const int near = g_stream_near >= 0 ? g_stream_near : ss.near_window;
+  kern<<<grid, WARPS * 32, smem_bytes, st>>>(a, s.d_spans, s.n_spans, ss.d_vptr, ss.d_vdst, (int)ss.n_v, near);
   return cudaGetLastError();
 }
 
@@ -278,22 +288,22 @@ static cudaError_t dispatch_stream(int vplmax, int variant, const SpmmArgs& a, c
 #define GCG_ST(V, VAR, D, W, MB, SM) \
   if (vplmax == V && variant == VAR) return launch_stream<V, D, W, MB, SM>(a, s, ss, st);
   // ---- 1 float4 per lane (<= 128 floats per panel)
-  GCG_ST(1, 1, 16, 16, 1, true)  GCG_ST(1, 2, 12, 16, 1, true)  GCG_ST(1, 3, 8, 16, 2, true)
+  GCG_ST(1, 1, 16, 16, 1, true)  GCG_ST(1, 2, 12, 32, 1, true)  GCG_ST(1, 3, 8, 16, 2, true)
   GCG_ST(1, 5, 8, 8, 3, false)   GCG_ST(1, 6, 4, 8, 4, false)
   // ---- 2 float4 per lane (<= 256 floats)
-  GCG_ST(2, 1, 12, 16, 1, true)  GCG_ST(2, 2, 8, 16, 1, true)   GCG_ST(2, 3, 6, 16, 2, true)
+  GCG_ST(2, 1, 12, 16, 1, true)  GCG_ST(2, 2, 8, 24, 1, true)   GCG_ST(2, 3, 6, 16, 2, true)
   GCG_ST(2, 5, 4, 8, 3, false)   GCG_ST(2, 6, 2, 8, 4, false)
   // ---- 3 float4 per lane (<= 384 floats)
-  GCG_ST(3, 1, 8, 16, 1, true)   GCG_ST(3, 2, 6, 16, 1, true)
+  GCG_ST(3, 1, 8, 16, 1, true)   GCG_ST(3, 2, 5, 24, 1, true)
   GCG_ST(3, 5, 3, 8, 3, false)   GCG_ST(3, 6, 2, 8, 3, false)
   // ---- 4 float4 per lane (<= 512 floats)
-  GCG_ST(4, 1, 6, 16, 1, true)   GCG_ST(4, 2, 5, 16, 1, true)
+  GCG_ST(4, 1, 6, 16, 1, true)   GCG_ST(4, 2, 4, 24, 1, true)
   GCG_ST(4, 5, 3, 8, 2, false)   GCG_ST(4, 6, 2, 8, 2, false)
   // ---- 5 float4 per lane (<= 640 floats: hidden 600)
-  GCG_ST(5, 1, 5, 16, 1, true)   GCG_ST(5, 2, 4, 16, 1, true)   GCG_ST(5, 3, 8, 8, 1, true)   GCG_ST(5, 4, 6, 12, 1, true)
-  GCG_ST(5, 5, 3, 8, 2, false)   GCG_ST(5, 7, 2, 8, 2, false)
+  GCG_ST(5, 1, 5, 16, 1, true)   GCG_ST(5, 2, 4, 16, 1, true)   GCG_ST(5, 3, 4, 20, 1, true)   GCG_ST(5, 4, 3, 24, 1, true)
+  GCG_ST(5, 5, 3, 8, 2, false)   GCG_ST(5, 7, 2, 8, 2, false)   GCG_ST(5, 8, 2, 32, 1, true)   GCG_ST(5, 9, 3, 28, 1, true)
   // ---- 8 float4 per lane (<= 1024 floats: 1024 regions)
-  GCG_ST(8, 1, 3, 16, 1, true)   GCG_ST(8, 2, 6, 8, 1, true)
+  GCG_ST(8, 1, 3, 16, 1, true)   GCG_ST(8, 2, 2, 24, 1, true)
   GCG_ST(8, 5, 2, 8, 2, false)
 #undef GCG_ST
   *found = false;
@@ -406,7 +416,12 @@ int spmm_stream_launch(const gcg_plan* p, SpmmArgs& a, cudaStream_t st) {
     if (rc != GCG_OK) return rc;
   }
   StreamState* s = mp->stream;
-  const int span_nnz = g_stream_span_nnz > 0 ? g_stream_span_nnz : 384;
+  // default span: 384 non-zeros, shorter for small matrices so that the grid still covers the 148 SMs twice over
+  int span_nnz = g_stream_span_nnz;
+  if (span_nnz <= 0) {
+    const int64_t nz = (int64_t)p->h_indptr[p->n_rows] - p->h_indptr[0];
+    span_nnz = (int)std::min<int64_t>(384, std::max<int64_t>(32, nz / (kNumSMs * 16 * 2)));
+  }
   StreamSchedule sched;
   {
     std::lock_guard<std::mutex> lk(s->mu);
@@ -447,9 +462,22 @@ int spmm_stream_launch(const gcg_plan* p, SpmmArgs& a, cudaStream_t st) {
 
 using namespace gcg;
 
-extern "C" void gcg_spmm_stream_tuning(int variant, int span_nnz) {
+extern "C" void gcg_spmm_stream_tuning(int variant, int span_nnz, int near_window) {
   gcg::g_stream_variant = variant;
   gcg::g_stream_span_nnz = span_nnz;
+  gcg::g_stream_near = near_window;
+}
+
+extern "C" int gcg_plan_set_near_window(gcg_plan* p, int32_t near_window_rows) {
+  GCG_CHECK_ARG(p != nullptr, "gcg_plan_set_near_window: plan is NULL");
+  GCG_CHECK_ARG(near_window_rows >= 0, "gcg_plan_set_near_window: negative window");
+  if (!p->stream) {
+    p->stream = new StreamState();
+    const int rc = build_vrows(p, p->stream);
+    if (rc != GCG_OK) return rc;
+  }
+  p->stream->near_window = near_window_rows;
+  return GCG_OK;
 }
 
 extern "C" int gcg_plan_set_schedule(gcg_plan* p, int64_t n_blocks, const int32_t* h_block_rows,

@@ -191,6 +191,10 @@ class _PhaseProfile:
 
 phase_profile = _PhaseProfile()
 
+import os as _os
+# feature-sliced propagation: second transpose fused into the SpMM epilogue (0 = separate gcg_push_rows_f32 pass)
+_FUSED_PUSH = _os.environ.get("GCG_DIST_FUSED_PUSH", "1") != "0"
+
 
 class _RawCudaArray:
     def __init__(self, ptr, numel):
@@ -212,19 +216,21 @@ class PeerBuffers:
         self.recv_floats = int(part.n_pad * fp_max)
         self.back_floats = int(P * rows_max * fp_max)
         self._own, handles = [], []
-        for nfl in (self.recv_floats, self.back_floats):
+        for nfl in (self.recv_floats, self.back_floats, 64):       # the third block: 64 int32 barrier flags (zeroed)
             ptr = C.c_void_p()
             h = C.create_string_buffer(64)
             _lib.check(L.gcg_peer_alloc(nfl * 4, C.byref(ptr), h), "gcg_peer_alloc")
             self._own.append(ptr.value)
             handles.append(h.raw)
+        torch.cuda.synchronize(part.device)        # the zero fill has landed before any peer can write a flag
         allh = [None] * P
         dist.all_gather_object(allh, handles, group=part.group)
-        self.recv_ptrs, self.back_ptrs, self._opened = [], [], []
+        self.recv_ptrs, self.back_ptrs, self.flag_ptrs, self._opened = [], [], [], []
         for q in range(P):
             if q == part.rank:
                 self.recv_ptrs.append(self._own[0])
                 self.back_ptrs.append(self._own[1])
+                self.flag_ptrs.append(self._own[2])
                 continue
             got = []
             for h in allh[q]:
@@ -234,16 +240,37 @@ class PeerBuffers:
                 self._opened.append(ptr.value)
             self.recv_ptrs.append(got[0])
             self.back_ptrs.append(got[1])
+            self.flag_ptrs.append(got[2])
         dev = part.device
         self.recv_t = torch.as_tensor(_RawCudaArray(self._own[0], self.recv_floats), device=dev)
         self.back_t = torch.as_tensor(_RawCudaArray(self._own[1], self.back_floats), device=dev)
         self._flag = torch.zeros(1, dtype=torch.float32, device=dev)
+        self._err = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._seq = 0
+        import os
+        self.nccl_barrier = os.environ.get("GCG_DIST_NCCL_BARRIER") == "1"
         self._C = C
         self._L = L
+        dist.barrier(group=part.group)             # every rank has mapped every buffer
 
     def barrier(self):
-        """cross-rank ordering point in stream order (tiny NCCL all-reduce; no host synchronisation)"""
-        dist.all_reduce(self._flag, group=self.part.group)
+        """cross-rank ordering point in stream order, no host synchronisation: peer-written flags waited on by
+        a one-warp kernel (gcg_peer_barrier); GCG_DIST_NCCL_BARRIER=1 selects the tiny NCCL all-reduce of round 1"""
+        if self.nccl_barrier:
+            dist.all_reduce(self._flag, group=self.part.group)
+            return
+        from . import _lib
+        C = self._C
+        self._seq += 1
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        _lib.check(self._L.gcg_peer_barrier(self.ptr_array(self.flag_ptrs), C.c_void_p(self._own[2]), self.part.world,
+                                            self.part.rank, self._seq, C.c_void_p(self._err.data_ptr()), stream),
+                   "gcg_peer_barrier")
+
+    def check(self):
+        """raise if a barrier gave up waiting for a peer (call at a host synchronisation point)"""
+        if int(self._err.item()) != 0:
+            raise RuntimeError("gcg_peer_barrier: a peer GPU did not arrive within the time limit")
 
     def ptr_array(self, ptrs, byte_offsets=None):
         C = self._C
@@ -368,18 +395,30 @@ class FeatureSplitCSRMatrix:
             bpad = self._buf("bias", (P * Fp,))
             bpad[:F].copy_(bias)
             bs = bpad[r * Fp:(r + 1) * Fp]
-        outslice = self._buf("outslice", (max(rows_total, 1), Fp))
-        if rows_total > 0:
-            ops.spmm(self.full, recv, out=outslice[:rows_total], bias=bs, act=act)
-        pp.mark("spmm")
-        # 2. row group of owner q goes to slot r of rank q's back buffer ([P][row_counts[q]][Fp])
+        # 2. the row group of owner q goes to slot r of rank q's back buffer ([P][row_counts[q]][Fp])
         off = np.zeros(P + 1, np.int64)
         np.cumsum(self.row_counts, out=off[1:])
         offs = (C.c_int64 * (P + 1))(*[int(x) for x in off])
         dst_ptrs = peer.ptr_array(peer.back_ptrs, [r * self.row_counts[q] * Fp * 4 for q in range(P)])
-        _lib.check(L.gcg_push_rows_f32(C.c_void_p(outslice.data_ptr()), offs, P, Fp, dst_ptrs, 0, stream),
-                   "gcg_push_rows_f32")
-        pp.mark("push_rows")
+        if _FUSED_PUSH:
+            # ... written by the SpMM's own epilogue stores (gcg_spmm_csr_routed_f32): the transfer over NVLink
+            # overlaps the gather instead of following it as a separate pass over the slice
+            if rows_total > 0:
+                A = self.full
+                rp, ldr = ops._mat(recv, "recv")
+                ws, wsb = ops.scratch.get(A.workspace_bytes(Fp), recv.device)
+                _lib.check(L.gcg_spmm_csr_routed_f32(A.plan, rp, ldr, Fp, P, dst_ptrs, offs, Fp,
+                                                     ops._vec(bs, "bias") if bs is not None else None,
+                                                     _lib.act_code(act), 0, ws, wsb, stream), "gcg_spmm_csr_routed_f32")
+            pp.mark("spmm+push_rows")
+        else:
+            outslice = self._buf("outslice", (max(rows_total, 1), Fp))
+            if rows_total > 0:
+                ops.spmm(self.full, recv, out=outslice[:rows_total], bias=bs, act=act)
+            pp.mark("spmm")
+            _lib.check(L.gcg_push_rows_f32(C.c_void_p(outslice.data_ptr()), offs, P, Fp, dst_ptrs, 0, stream),
+                       "gcg_push_rows_f32")
+            pp.mark("push_rows")
         peer.barrier()
         pp.mark("barrier2")
         if my_rows == 0:

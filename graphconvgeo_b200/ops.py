@@ -22,6 +22,11 @@ from .sparse import CSRMatrix
 # more than the hits save, so panel mode is OFF by default (budget 0) and selected explicitly.
 L2_PANEL_BUDGET_BYTES = int(os.environ.get("GCG_L2_PANEL_BUDGET", 0))
 _FORCE_PANEL = os.environ.get("GCG_SPMM_PANEL")          # experiments: force panel_cols
+# which SpMM kernel family runs when the caller does not say: "auto" = the nnz-balanced streaming kernel
+# (csrc/gcg_spmm_stream.cu) for matrices with >= STREAM_MIN_NNZ non-zeros, the register-gather kernel below that
+# (measured on B200, Twitter-World A_hat.H at F = 600: 7.65 ms streaming vs 12.5 ms register-gather)
+_SPMM_MODE = os.environ.get("GCG_SPMM_MODE", "auto")     # "auto" | "stream" | "gather"
+STREAM_MIN_NNZ = int(os.environ.get("GCG_STREAM_MIN_NNZ", 1 << 20))
 _GEMM_MODE = os.environ.get("GCG_GEMM_MODE", "auto")     # "fma" | "tf32x3" | "tf32" | "auto"
 
 _tc_available = None
@@ -96,9 +101,19 @@ scratch = _Scratch()
 
 
 # --------------------------------------------------------------------- SpMM
-def auto_panel_cols(n_cols, F):
+STREAM_MIN_F = int(os.environ.get("GCG_STREAM_MIN_F", 320))
+
+
+def auto_panel_cols(n_cols, F, nnz=0, prefer=None):
+    """Kernel family for an SpMM the caller did not pin.  Measured on B200 (profiles/r02_spmm_stream.md), rows of
+    the Twitter-World A_hat: the streaming kernel wins for wide operands gathered from HBM (F = 600: 7.7 vs 12.5
+    ms, F = 1024: 14.0 vs 22.1), ties at F = 256 and loses for narrow ones (F = 76: 3.4 vs 2.7) and for operands
+    that sit in L2 / L1 (the document blocks of X^T.dZ1: 1.9 vs 1.0 ms), which ``prefer="gather"`` marks."""
     if _FORCE_PANEL is not None:
         return int(_FORCE_PANEL)
+    mode = _SPMM_MODE if _SPMM_MODE != "auto" else (prefer or "auto")
+    if F <= 1024 and (mode == "stream" or (mode == "auto" and nnz >= STREAM_MIN_NNZ and F >= STREAM_MIN_F)):
+        return -2
     if L2_PANEL_BUDGET_BYTES <= 0 or n_cols * F * 4 <= L2_PANEL_BUDGET_BYTES:
         return 0
     p = 16
@@ -134,7 +149,7 @@ def spmm(A: CSRMatrix, B, out=None, bias=None, act="identity", accumulate=False,
         if conv_out is not None:
             vp, ldv = _mat(conv_out, "conv_out")
     if panel_cols is None:
-        panel_cols = auto_panel_cols(k, F)
+        panel_cols = auto_panel_cols(k, F, A.nnz, getattr(A, "spmm_mode", None))
     ws, wsb = scratch.get(A.workspace_bytes(ldc), B.device)
     _lib.check(L.gcg_spmm_csr_f32(A.plan, bp, ldb, F, cp, ldc, _vec(bias, "bias"), _lib.act_code(act),
                                   int(bool(accumulate)), gp, ldg, hp, ldh, vp, ldv, int(panel_cols), ws, wsb,

@@ -486,6 +486,7 @@ class BlockedRows:
             hip = o_ip[b * (n_sel + 1):(b + 1) * (n_sel + 1)]
             blk = CSRMatrix(dev_ip[b * (n_sel + 1):(b + 1) * (n_sel + 1)], dev_ix[a:e], dev_d[a:e], (n_sel, N),
                             host=(hip, None, None), long_row_threshold=XT.long_row_threshold)
+            blk.spmm_mode = "gather"          # the block of dZ rows it gathers from is L2-resident by construction
             self.blocks.append(blk)
         self.heavy_dev = torch.from_numpy(self.heavy_ids.astype(np.int64)).to(self.device)
         self._tmp = None

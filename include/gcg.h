@@ -129,9 +129,14 @@ int gcg_spmm_csr_f32(const gcg_plan* plan, const float* B, int64_t ldb, int64_t 
  * Replaces: nothing in the reference; B200-side preparation for S.dot, lasagne_layers.py:67,84. */
 int gcg_plan_set_schedule(gcg_plan* plan, int64_t n_blocks, const int32_t* h_block_rows,
                           const int32_t* h_block_panels);
+/* L2 residency hint of the streaming variant for a square matrix whose node order keeps communities together:
+ * gathered rows whose column lies within near_window_rows of the gathering row are loaded with the L2 evict_last
+ * policy (the reusable set), all others with evict_first (long-range edges are never re-read before eviction and
+ * would only push the reusable set out).  0 = every gather evict_last (default). */
+int gcg_plan_set_near_window(gcg_plan* plan, int32_t near_window_rows);
 /* experiment knobs of the streaming variant: kernel variant (0 = default of the width class; 1-4 shared-memory
- * ring depths, 5-8 register pipelines) and non-zeros per span (0 = 384) */
-void gcg_spmm_stream_tuning(int variant, int span_nnz);
+ * ring depths, 5-8 register pipelines), non-zeros per span (0 = 384), near window (-1 = the plan's) */
+void gcg_spmm_stream_tuning(int variant, int span_nnz, int near_window);
 
 /* ------------------------------------------------------------------- GEMM */
 
@@ -242,6 +247,21 @@ int gcg_peer_alloc(int64_t bytes, void** d_ptr, void* handle64);
 int gcg_peer_free(void* d_ptr);
 int gcg_peer_open(const void* handle64, void** d_ptr);
 int gcg_peer_close(void* d_ptr);
+/* Cross-GPU barrier in stream order (no collective launch): stores `seq` into slot `rank` of every peer's int32
+ * flag array (system-scope fence first: peer stores of earlier kernels on this stream become visible before it),
+ * then waits until all P slots of the own array reached `seq`.  seq must grow by one per call on every rank.
+ * A peer that never arrives sets *err_flag (device int32) after ~4 s instead of hanging the GPU. */
+int gcg_peer_barrier(void* const* h_peer_flags, void* own_flags, int32_t P, int32_t rank, int32_t seq,
+                     void* err_flag, void* stream);
+/* gcg_spmm_csr_f32 whose output rows are ROUTED to their owners: row r with owner_row_off[q] <= r <
+ * owner_row_off[q+1] is written to owner_base[q] + (r - owner_row_off[q]) * ldc.  With peer-mapped owner buffers
+ * the second transpose of the feature-sliced propagation (push_rows) rides on the SpMM's own epilogue stores:
+ * NVLink traffic overlaps the gather instead of following it.  Same summation order as gcg_spmm_csr_f32
+ * (S.dot, lasagne_layers.py:67,84); bias + activation fused, no gate / accumulate. */
+int gcg_spmm_csr_routed_f32(const gcg_plan* plan, const float* B, int64_t ldb, int64_t F, int32_t n_owner,
+                            void* const* h_owner_base, const int64_t* h_owner_row_off, int64_t ldc,
+                            const float* bias, int act, int32_t panel_cols, void* workspace,
+                            int64_t workspace_bytes, void* stream);
 int gcg_push_cols_f32(const float* src, int64_t ld, int64_t n_rows, int64_t F, int32_t P, int64_t Fp,
                       void* const* h_peer_dst, int64_t dst_row0, void* stream);
 int gcg_push_rows_f32(const float* src, const int64_t* h_row_off, int32_t P, int64_t Fp,

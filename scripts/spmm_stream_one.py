@@ -21,6 +21,7 @@ ap.add_argument("--variant", type=int, default=0, help="-1: register-gather kern
 ap.add_argument("--span", type=int, default=384)
 ap.add_argument("--schedule", default="rows", help="rows | inter<k> | l2:<MB>")
 ap.add_argument("--reps", type=int, default=6)
+ap.add_argument("--near", type=int, default=-1, help="near window in rows (evict_last inside, evict_first outside)")
 args = ap.parse_args()
 dev = torch.device("cuda")
 wl = synth.make_workload_device(args.workload, device=dev, seed=77)
@@ -38,7 +39,7 @@ if args.schedule.startswith("inter"):
 elif args.schedule.startswith("l2:"):
     A.set_schedule(*l2_schedule(A, args.F, budget_bytes=int(args.schedule[3:]) << 20))
 panel = 0 if args.variant < 0 else -2
-_lib.lib().gcg_spmm_stream_tuning(max(args.variant, 0), args.span)
+_lib.lib().gcg_spmm_stream_tuning(max(args.variant, 0), args.span, args.near)
 ts = []
 for _ in range(args.reps):
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -39,7 +39,9 @@ def main():
     ap.add_argument("--F", type=int, nargs="+", default=[600])
     ap.add_argument("--variants", type=int, nargs="+", default=[1, 2, 3, 4, 5, 6, 7])
     ap.add_argument("--spans", type=int, nargs="+", default=[384])
+    ap.add_argument("--near", type=int, nargs="+", default=[0], help="near windows (rows) to try")
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--rows-only", action="store_true", help="whole-row schedule only")
     args = ap.parse_args()
     dev = torch.device("cuda")
     L = _lib.lib()
@@ -76,12 +78,12 @@ def main():
         vpl = -(-f4 // 32)
         n_full = max(1, -(-f4 // 32))
         scheds = [("whole rows", None)]
-        if vpl > 1:
+        if vpl > 1 and not args.rows_only:
             scheds.append(("interleaved %d x 128-float panels" % n_full, ([0, n], [-n_full])))
             if vpl >= 4:
                 scheds.append(("interleaved 2 panels", ([0, n], [-2])))
         rep = []
-        for budget in ((32, 48, 80) if not args.quick else (48,)):
+        for budget in (() if args.rows_only else (32, 48, 80) if not args.quick else (48,)):
             br, bp = l2_schedule(A, F, budget_bytes=budget << 20, report=rep)
             if bp.max() > 1:
                 scheds.append(("l2 tiling budget %d MB: %d blocks, panels hist %s" % (budget, len(bp), np.bincount(bp).tolist()), (br, bp)))
@@ -89,18 +91,18 @@ def main():
         for sname, sch in scheds:
             A.set_schedule(*(sch if sch is not None else (None, None)))
             for span in args.spans:
-                for var in args.variants:
-                    L.gcg_spmm_stream_tuning(var, span)
+                for var, near in [(v_, n_) for v_ in args.variants for n_ in args.near]:
+                    L.gcg_spmm_stream_tuning(var, span, near)
                     try:
                         got = ops.spmm(A, H, out=out, panel_cols=-2)
                         ok = bool(torch.equal(got, ref))
                         emit("stream", F, *timeit(lambda: ops.spmm(A, H, out=out, panel_cols=-2)), variant=var, span=span,
-                             schedule=sname, bit_identical=ok)
+                             near=near, schedule=sname, bit_identical=ok)
                     except Exception as e:      # noqa: BLE001
-                        print(json.dumps({"tag": "stream", "F": F, "variant": var, "span": span, "schedule": sname,
+                        print(json.dumps({"tag": "stream", "F": F, "variant": var, "span": span, "near": near, "schedule": sname,
                                           "error": str(e)[:200]}), flush=True)
                     finally:
-                        L.gcg_spmm_stream_tuning(0, 0)
+                        L.gcg_spmm_stream_tuning(0, 0, -1)
         A.set_schedule(None)
         del H, out, ref
         torch.cuda.empty_cache()

@@ -23,9 +23,14 @@ def gpu_main():
     import datetime
     dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=120))
     w = synth.make_workload("tiny")
-    for n_layers, highway, reorder, partition, peer in ((2, False, None, "row", False), (3, True, "labels", "row", False),
-                                                         (2, False, "labels", "feature", False), (3, True, None, "feature", False),
-                                                         (3, True, "labels", "feature", True), (2, False, None, "feature", True)):
+    # the last case runs with drop_out=True and p = 0: the DropoutLayer sits in the chain (its branch of the
+    # backward must hand the layer below a gradient w.r.t. the ACTIVATION, so relu' is applied there) while the
+    # masks are the identity, so the oracle without dropout is the reference
+    for n_layers, highway, reorder, partition, peer, drop in (
+            (2, False, None, "row", False, False), (3, True, "labels", "row", False, False),
+            (2, False, "labels", "feature", False, False), (3, True, None, "feature", False, False),
+            (3, True, "labels", "feature", True, False), (2, False, None, "feature", True, False),
+            (3, True, None, "row", False, True), (2, False, "labels", "feature", True, True)):
         rng = np.random.RandomState(5)
         params = go.init_params(rng, w.X.shape[1], w.hidden, w.n_classes, n_layers, highway)
         idx = rng.choice(w.train_indices, size=len(w.train_indices)).astype(np.int32)      # duplicates
@@ -35,7 +40,7 @@ def gpu_main():
         hist = go.train_epochs(net, ref_params, idx, y, 3)
         m = DistMLPCONV(n_epochs=1, regul_coefs=[1e-4, 2e-4], hidden_layer_size=w.hidden, n_layers=n_layers,
                         highway=highway, init_parameters=[p.copy() for p in params], device=dev, reorder=reorder,
-                        partition=partition, peer_memory=peer)
+                        partition=partition, peer_memory=peer, drop_out=drop, dropout_coefs=[0.0, 0.0])
         m.prepare(w.X, idx, w.dev_indices, w.test_indices, w.Y, w.A_hat)
         assert m.part.world == world
         for step in range(3):
@@ -45,7 +50,8 @@ def gpu_main():
             assert abs(a - hist[step][1]) <= 2.0 / len(idx)
             if step == 0:       # activations of the first step, gathered over ranks, original node order
                 c = net.forward(params, idx)
-                for i, ly in enumerate(m.layers[:-1]):
+                conv_layers = [ly for ly in m.layers[:-1] if hasattr(ly, "W")]
+                for i, ly in enumerate(conv_layers):
                     assert_close(m.node_rows(ly._out), c["A"][i], what="activation %d" % i)
         for p_gpu, p in zip(m.get_param_values(), ref_params):
             assert_close(p_gpu, p, atol=1e-5, rtol=1e-3, what="params after 3 steps")
@@ -62,7 +68,10 @@ def gpu_main():
         _, ref_acc = net.loss_acc(ref_params, w.test_indices, w.Y[w.test_indices].astype(np.int32))
         assert abs(acc - ref_acc) <= 2.0 / len(w.test_indices)
         if rank == 0:
-            print("dist case", n_layers, highway, reorder, partition, "peer" if (peer and m.part.peer is not None) else "nccl", "OK", flush=True)
+            print("dist case", n_layers, highway, reorder, partition, "peer" if (peer and m.part.peer is not None) else "nccl",
+                  "dropout(p=0)" if drop else "", "OK", flush=True)
+        if m.part.peer is not None:
+            m.part.peer.check()
     dist.barrier()
     dist.destroy_process_group()
     if rank == 0:

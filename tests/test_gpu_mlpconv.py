@@ -160,8 +160,17 @@ def test_geotext_shape_reference_network_step():
         m.f_train()
         l_gpu, a_gpu = m.train_results()
         assert abs(l_gpu - float(loss)) <= 1e-5 * abs(float(loss))
+        flips = 0
         for i, ly in enumerate(m.layers[:-1]):
             assert_close(m.node_rows(ly._out), cache["A"][i], what="activation %d" % i)
+            pre_gpu = m.node_rows(ly._Hc) if getattr(ly, "_Hc", None) is not None else m.node_rows(ly._out)
+            pre_ref = cache["Hc"][i] if cache["Hc"][i] is not None else cache["A"][i]
+            flips += int(np.count_nonzero((pre_gpu > 0) != (pre_ref > 0)))
+        # Node reordering permutes the columns of A_hat, hence the CSR summation order inside a row: a
+        # pre-activation within an ulp of zero can land on the other side of the relu kink, and relu' then differs
+        # for that ONE element (both evaluations are valid float32).  Each such flip moves a gradient entry by at
+        # most |dO| of that element (~1e-6 here), so the bound is widened by that much per flip -- only then.
+        atol = 1e-6 + 2e-6 * flips
         gpu_grads = m.get_grad_values()
         k = 0
         for ly in m.layers:
@@ -169,7 +178,7 @@ def test_geotext_shape_reference_network_step():
                 g = gpu_grads[k]
                 if tags.get("regularizable"):
                     g = g + np.float32(0.5e-6) * (np.sign(params[k]) + np.float32(2) * params[k])
-                assert_close(g, grads[k], what="grad %d" % k)
+                assert_close(g, grads[k], atol=atol, what="grad %d (%d relu flips)" % (k, flips))
                 k += 1
 
 

@@ -37,6 +37,7 @@ def test_small_model_every_operation_within_tolerance(n_layers, highway):
     rep, lines = run_check(m, n_rows=400, n_param_rows=16)
     assert rep["n_checks"] >= (14 if n_layers == 2 else 28)
     assert rep["max_scaled_err"] <= 1.0, "\n".join(lines)
+    assert rep["max_err_over_ref_max"] <= 1e-4, rep["worst_relative_check"]
 
 
 def test_checker_detects_a_wrong_gradient(monkeypatch):
@@ -83,3 +84,6 @@ def test_benched_configuration_every_operation_within_tolerance(name):
     rep, lines = run_check(m, steps_before=2, n_rows=1024, n_param_rows=16)
     print("\n".join(lines))
     assert rep["max_scaled_err"] <= 1.0, "\n".join(l for l in lines if "scaled" in l)
+    # the absolute term of the bound swallows the tiny gradients of a mean over ~1M targets: every array must also
+    # agree to 1e-3 of its own largest value (tcgen05 3xTF32 chains: ~3e-5; float32 sums of 1.4 M terms: ~1e-5)
+    assert rep["max_err_over_ref_max"] <= 1e-3, rep["worst_relative_check"]

@@ -113,7 +113,7 @@ def test_streaming_variants_are_bit_exact(variant):
     L = _lib.lib()
     try:
         for span in (32, 100, 384):
-            L.gcg_spmm_stream_tuning(variant, span)
+            L.gcg_spmm_stream_tuning(variant, span, -1)
             for F in STREAM_F:
                 B = rng.standard_normal((700, F)).astype(np.float32)
                 b = rng.standard_normal(F).astype(np.float32)
@@ -124,7 +124,7 @@ def test_streaming_variants_are_bit_exact(variant):
                 short = np.diff(A.indptr) <= 64
                 assert np.array_equal(got[short], ref[short]), (variant, span, F)   # and as scipy, unsplit rows
     finally:
-        L.gcg_spmm_stream_tuning(0, 0)
+        L.gcg_spmm_stream_tuning(0, 0, -1)
 
 
 @pytest.mark.parametrize("sched", [([0, 1000], [3]), ([0, 1000], [-5]), ([0, 10, 10, 400, 1000], [1, 4, -2, 6]),
@@ -135,7 +135,7 @@ def test_streaming_block_panel_schedules_are_bit_exact(sched):
     rng = np.random.RandomState(7)
     A = random_csr(rng, 1000, 800, 9, hub_rows=(0, 500), hub_deg=700)
     Ad = CSRMatrix.from_scipy(A, "cuda", long_row_threshold=128)
-    _lib.lib().gcg_spmm_stream_tuning(0, 64)
+    _lib.lib().gcg_spmm_stream_tuning(0, 64, -1)
     try:
         for F in (24, 300, 600, 930):
             B = to_dev(rng.standard_normal((800, F)).astype(np.float32))
@@ -145,7 +145,7 @@ def test_streaming_block_panel_schedules_are_bit_exact(sched):
             Ad.set_schedule(*sched)
             assert torch.equal(ops.spmm(Ad, B, panel_cols=-2), want), (sched, F)
     finally:
-        _lib.lib().gcg_spmm_stream_tuning(0, 0)
+        _lib.lib().gcg_spmm_stream_tuning(0, 0, -1)
     with pytest.raises(_lib.GcgError):
         Ad.set_schedule([0, 500], [1])                       # does not cover all rows
 
