@@ -688,7 +688,7 @@ def spmm_roofline(m, wl, dev, reps=10):
     others = None
     if not dist_mode:
         # the two other sparse products of the epoch against their own compulsory traffic
-        from graphconvgeo_b200.lasagne_layers import _xt_product
+        from graphconvgeo_b200.lasagne_layers import _x_product, _xt_product
         l1 = m.l_hid1
         X = m.Xd
         V = X.shape[1]
@@ -707,11 +707,14 @@ def spmm_roofline(m, wl, dev, reps=10):
                 e.synchronize()
                 ts.append(s.elapsed_time(e))
             return float(np.mean(ts))
-        t_xw = timed(lambda: ops.spmm(X, l1.W, out=z))
+        t_xw = timed(lambda: _x_product(l1, X, l1.W, z))
         t_xt = timed(lambda: _xt_product(l1, X, H, dW))
         b_xw = 8 * X.nnz + 4 * (N + 1) + 4 * V * F + 4 * N * F
         b_xt = 8 * X.nnz + 4 * (V + 1) + 4 * N * F + 4 * V * F
-        others = [{"kernel": "X.W1 (a1): CSR [%d x %d] nnz %d times dense [%d x %d]" % (N, V, X.nnz, V, F), "ms": t_xw,
+        others = [{"kernel": "X.W1 (a1): CSR [%d x %d] nnz %d times dense [%d x %d]%s" % (
+                       N, V, X.nnz, V, F, (" (dense head of %d terms = %.0f%% of the non-zeros on tcgen05 + sparse tail)"
+                                            % (l1._x_head[1].k_head, 100 * l1._x_head[1].head_fraction))
+                       if getattr(l1, "_x_head", None) is not None else ""), "ms": t_xw,
                    "algorithmic_bytes": b_xw, "achieved": b_xw / t_xw / 1e6, "frac": b_xw / t_xw / 1e6 / peak, "unit": "GB/s",
                    "gathered_TBps": 4.0 * X.nnz * F / t_xw / 1e9},
                   {"kernel": "X^T.dZ1 (a6): document-blocked CSR of X^T [%d x %d] times dense [%d x %d]" % (V, N, N, F), "ms": t_xt,

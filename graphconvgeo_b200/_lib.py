@@ -24,7 +24,7 @@ STATUS = {0: "GCG_OK", -1: "GCG_ERR_BAD_ARG", -2: "GCG_ERR_SHAPE", -3: "GCG_ERR_
           -4: "GCG_ERR_NCCL", -5: "GCG_ERR_NOMEM", -6: "GCG_ERR_UNSUPPORTED"}
 
 ACT = {"identity": 0, "linear": 0, None: 0, "rectify": 1, "relu": 1, "tanh": 2, "sigmoid": 3}
-GEMM_MODE = {"fma": 0, "tf32x3": 1, "tf32": 2}
+GEMM_MODE = {"fma": 0, "tf32x3": 1, "tf32": 2, "tf32x3_chained": 3}
 
 # name -> (restype, argtypes); mirrors include/gcg.h one to one
 PROTOTYPES = {
@@ -87,6 +87,7 @@ PROTOTYPES = {
     "gcg_spmm_csr_routed_f32": (c_int, [c_vp, c_vp, c_i64, c_i64, c_i32, C.POINTER(c_vp), C.POINTER(c_i64), c_i64, c_vp,
                                         c_int, c_i32, c_vp, c_i64, c_vp]),
     "gcg_spmm_set_tuning": (None, [c_int, c_int]),
+    "gcg_spmm_set_group": (None, [c_int, c_int]),
     "gcg_plan_set_schedule": (c_int, [c_vp, c_i64, c_vp, c_vp]),
     "gcg_spmm_stream_tuning": (None, [c_int, c_int, c_int]),
     "gcg_plan_set_near_window": (c_int, [c_vp, c_i32]),

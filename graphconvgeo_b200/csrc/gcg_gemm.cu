@@ -230,7 +230,7 @@ static int gemm_impl(int transA, int transB, int64_t M, int64_t N, int64_t K, co
                   (long long)lda, (long long)ldb, (long long)ldc);
   GCG_CHECK_ARG(act >= GCG_ACT_IDENTITY && act <= GCG_ACT_SIGMOID, "gcg_gemm_f32: bad act %d", act);
   GCG_CHECK_ARG(!mask || ld_mask >= N, "gcg_gemm_f32: ld_mask too small");
-  GCG_CHECK_ARG(mode == GCG_GEMM_FMA || mode == GCG_GEMM_TF32X3 || mode == GCG_GEMM_TF32,
+  GCG_CHECK_ARG(mode == GCG_GEMM_FMA || mode == GCG_GEMM_TF32X3 || mode == GCG_GEMM_TF32 || mode == GCG_GEMM_TF32X3_CHAINED,
                 "gcg_gemm_f32: unknown mode %d", mode);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (M == 0 || N == 0) return GCG_OK;

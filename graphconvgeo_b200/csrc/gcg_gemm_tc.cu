@@ -560,7 +560,7 @@ int64_t gemm_tc_workspace_bytes(int transA, int transB, int64_t M, int64_t N, in
   // callers with larger leading dimensions get the FFMA fallback if the workspace is short
   if (split_k <= 0) split_k = gemm_tc_auto_split(M, N, K);
   int64_t b = 0;
-  if (mode == GCG_GEMM_TF32X3) {
+  if (mode == GCG_GEMM_TF32X3 || mode == GCG_GEMM_TF32X3_CHAINED) {
     const int64_t a_el = (transA ? K : M) * (((transA ? M : K) + 3) / 4 * 4);
     const int64_t b_el = (transB ? N : K) * (((transB ? K : N) + 3) / 4 * 4);
     b += 2 * round16(a_el * 4) + 2 * round16(b_el * 4);     // hi and lo copies of both operands
@@ -574,7 +574,7 @@ int gemm_tc_launch(const GemmArgs& g0, int transA, int transB, int mode, void* w
   if (!encode_fn()) return GCG_ERR_UNSUPPORTED;
   GemmArgs g = g0;
   if (!(g.vecA && g.vecB) || g.K < 1) return GCG_ERR_UNSUPPORTED;
-  const int x3 = (mode == GCG_GEMM_TF32X3);
+  const int x3 = (mode == GCG_GEMM_TF32X3 || mode == GCG_GEMM_TF32X3_CHAINED);
   const int64_t a_rows = transA ? g.K : g.M, a_cols = transA ? g.M : g.K;
   const int64_t b_rows = transB ? g.N : g.K, b_cols = transB ? g.K : g.N;
   // carve the workspace
@@ -641,10 +641,13 @@ int gemm_tc_launch(const GemmArgs& g0, int transA, int transB, int mode, void* w
   ta.num_kb_total = num_kb;
   ta.kb_per_split = kbps;
   ta.x3 = x3;
-  // 3xTF32: accumulation chains of at most 8 K blocks (K = 256): 32 truncating adds into the hi.hi accumulator
+  // 3xTF32: accumulation chains of at most 4 K blocks (K = 128): 16 truncating adds into the hi.hi accumulator
   // instead of 75 at K = 600 (measured at Twitter-World: logits error 2.1x -> 1.0x -> below the 1e-4 bound)
-  static const int chunk_env = getenv("GCG_GEMM_CHUNK_KB") ? atoi(getenv("GCG_GEMM_CHUNK_KB")) : 8;
-  ta.chunk_kb = (x3 && chunk_env > 0 && kbps > chunk_env) ? chunk_env : 0;
+  // measured in the Twitter-World epoch: chains of 4 K blocks everywhere cost +15 ms of 55 ms of GEMMs (the epilogue
+  // warps drain TMEM once per chain), so only callers that ask for it (GCG_GEMM_TF32X3_CHAINED) get short chains
+  static const int chunk_env = getenv("GCG_GEMM_CHUNK_KB") ? atoi(getenv("GCG_GEMM_CHUNK_KB")) : 0;
+  const int chunk = (mode == GCG_GEMM_TF32X3_CHAINED) ? 4 : chunk_env;
+  ta.chunk_kb = (x3 && chunk > 0 && kbps > chunk) ? chunk : 0;
   const int64_t total = (int64_t)ta.m_tiles * ta.n_tiles * split;
   if (total >= INT32_MAX) return GCG_ERR_UNSUPPORTED;
   const int smem_bytes = (x3 ? 3 * 4 : 6 * 2) * TILE_BYTES + 1024 + 256;

@@ -22,6 +22,7 @@
 //     caller sizes to stay resident in the 126 MB L2 (evict_last on gathers).
 //   * Epilogue fused: +bias, relu/tanh/sigmoid, highway mix g*Hc + (1-g)*H.
 #include <algorithm>
+#include <cstdlib>
 #include <map>
 #include <mutex>
 #include <vector>
@@ -384,6 +385,7 @@ cudaError_t spmm_finalize_launch(const SpmmArgs& a, int n_long, cudaStream_t st)
 }
 
 static int g_tune_u = 0, g_tune_minb = 0;   // experiment knobs (gcg_spmm_set_tuning); 0 = defaults
+static int g_tune_g = 0, g_tune_vpl = 0;    // experiment knob (gcg_spmm_set_group): lanes per row x float4 per lane
 
 template <int G, int VPL>
 static cudaError_t launch_vec(const SpmmArgs& a, cudaStream_t st) {
@@ -407,6 +409,7 @@ static cudaError_t launch_vec(const SpmmArgs& a, cudaStream_t st) {
 using namespace gcg;
 
 extern "C" void gcg_spmm_set_tuning(int u, int minb) { gcg::g_tune_u = u; gcg::g_tune_minb = minb; }
+extern "C" void gcg_spmm_set_group(int lanes, int vpl) { gcg::g_tune_g = lanes; gcg::g_tune_vpl = vpl; }
 
 extern "C" int gcg_plan_create_csr(int64_t n_rows, int64_t n_cols, int64_t nnz,
                                    const int32_t* d_indptr, const int32_t* d_indices,
@@ -677,6 +680,11 @@ static int spmm_run(const gcg_plan* p, const float* B, int64_t ldb, int64_t F,
   else if (want_f4 <= 8) { G = 8; VPL = 1; }
   else if (want_f4 <= 16) { G = 16; VPL = 1; }
   else { G = 32; VPL = (int)std::min<int64_t>(5, ceil_div(want_f4, 32)); }   // (8,3)/(16,2) groups measured slower than (32,1) at f4 = 19
+  // narrow operands (the F/P column slices of the multi-GPU propagation: 19 float4 at P = 8): a 32-lane group
+  // leaves 13 lanes idle; 4 lanes x 5 float4 (8 rows per warp) use all of them
+  static const bool narrow_groups = getenv("GCG_SPMM_NARROW_GROUPS") ? atoi(getenv("GCG_SPMM_NARROW_GROUPS")) != 0 : false;
+  if (narrow_groups && panel_cols == 0 && want_f4 > 16 && want_f4 <= 20) { G = 4; VPL = 5; }
+  if (panel_cols == 0 && g_tune_g > 0 && g_tune_g * g_tune_vpl >= want_f4) { G = g_tune_g; VPL = g_tune_vpl; }
   a.panel_f4 = G * VPL;
   a.n_panels = (int)ceil_div(a.f4_total, a.panel_f4);
   const int rpb = 8 * (32 / G);
@@ -689,6 +697,11 @@ static int spmm_run(const gcg_plan* p, const float* B, int64_t ldb, int64_t F,
     case 4 * 8 + 1: e = launch_vec<4, 1>(a, st); break;
     case 8 * 8 + 1: e = launch_vec<8, 1>(a, st); break;
     case 16 * 8 + 1: e = launch_vec<16, 1>(a, st); break;
+    case 4 * 8 + 5: e = launch_vec<4, 5>(a, st); break;
+    case 4 * 8 + 3: e = launch_vec<4, 3>(a, st); break;
+    case 8 * 8 + 3: e = launch_vec<8, 3>(a, st); break;
+    case 8 * 8 + 2: e = launch_vec<8, 2>(a, st); break;
+    case 16 * 8 + 2: e = launch_vec<16, 2>(a, st); break;
     case 32 * 8 + 1: e = launch_vec<32, 1>(a, st); break;
     case 32 * 8 + 2: e = launch_vec<32, 2>(a, st); break;
     case 32 * 8 + 3: e = launch_vec<32, 3>(a, st); break;

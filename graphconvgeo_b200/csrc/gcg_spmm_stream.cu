@@ -96,11 +96,21 @@ __device__ __forceinline__ void epilogue_store_lean(const SpmmArgs& a, int64_t r
   stg_f4_stream(reinterpret_cast<float4*>(out_row_ptr(a, row) + 4 * (int64_t)c4), v, strm);
 }
 
+// C += v, nothing else: the column-blocked products (X^T.dZ1 one document block at a time) accumulate into a
+// compact buffer that is re-read soon -> default cache policy, no streaming hint
+__device__ __forceinline__ void epilogue_accumulate_only(const SpmmArgs& a, int64_t row, int c4, float4 v) {
+  float4* cp = reinterpret_cast<float4*>(out_row_ptr(a, row) + 4 * (int64_t)c4);
+  const float4 o = *cp;
+  v.x = __fadd_rn(o.x, v.x); v.y = __fadd_rn(o.y, v.y);
+  v.z = __fadd_rn(o.z, v.z); v.w = __fadd_rn(o.w, v.w);
+  *cp = v;
+}
+
 // One warp = one span.  VPLMAX float4 per lane and row, D = pipeline depth (ring slots / register rows),
 // SMEM = transport.  Iteration t issues the gather of non-zero t and consumes non-zero t - (D - 1); the loop
 // runs D - 1 iterations past the span's last non-zero so that the last rows drain through the same (single)
 // row-flush site.
-template <int VPLMAX, int D, bool SMEM, bool LEAN>
+template <int VPLMAX, int D, bool SMEM, int LEAN>
 __device__ __forceinline__ void spmm_stream_body(const SpmmArgs& a, const StreamSpan* __restrict__ spans, int n_spans,
                                                  const int* __restrict__ vptr, const int* __restrict__ vdst, int n_v,
                                                  int warps_per_cta, int near_window) {
@@ -156,7 +166,8 @@ __device__ __forceinline__ void spmm_stream_body(const SpmmArgs& a, const Stream
 #pragma unroll
         for (int j = 0; j < VPLMAX; ++j)
           if (cv[j]) {
-            if (LEAN) epilogue_store_lean(a, dst, f4_beg + lane + 32 * j, acc[j], strm);
+            if (LEAN == 1) epilogue_store_lean(a, dst, f4_beg + lane + 32 * j, acc[j], strm);
+            else if (LEAN == 2) epilogue_accumulate_only(a, dst, f4_beg + lane + 32 * j, acc[j]);
             else epilogue_store(a, dst, f4_beg + lane + 32 * j, acc[j], strm);
           }
       }
@@ -247,7 +258,7 @@ __device__ __forceinline__ void spmm_stream_body(const SpmmArgs& a, const Stream
   while (v < v_end) flush_row();                         // spans made of empty rows only
 }
 
-template <int VPLMAX, int D, int WARPS, int MINB, bool SMEM, bool LEAN>
+template <int VPLMAX, int D, int WARPS, int MINB, bool SMEM, int LEAN>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 spmm_stream_kernel(const SpmmArgs a, const StreamSpan* __restrict__ spans, int n_spans, const int* __restrict__ vptr,
                    const int* __restrict__ vdst, int n_v, int near_window) {
@@ -255,7 +266,7 @@ spmm_stream_kernel(const SpmmArgs a, const StreamSpan* __restrict__ spans, int n
 }
 
 // ------------------------------------------------------------------------------------------ host side
-template <int VPLMAX, int D, int WARPS, int MINB, bool SMEM, bool LEAN>
+template <int VPLMAX, int D, int WARPS, int MINB, bool SMEM, int LEAN>
 static cudaError_t launch_stream_epi(const SpmmArgs& a, const StreamSchedule& s, const StreamState& ss, cudaStream_t st) {
   auto kern = spmm_stream_kernel<VPLMAX, D, WARPS, MINB, SMEM, LEAN>;
   const int smem_bytes = SMEM ? WARPS * D * VPLMAX * 512 : 0;
@@ -276,8 +287,10 @@ static cudaError_t launch_stream_epi(const SpmmArgs& a, const StreamSchedule& s,
 template <int VPLMAX, int D, int WARPS, int MINB, bool SMEM>
 static cudaError_t launch_stream(const SpmmArgs& a, const StreamSchedule& s, const StreamState& ss, cudaStream_t st) {
   const bool lean = a.act <= GCG_ACT_RELU && !a.gate && !a.accumulate;
-  return lean ? launch_stream_epi<VPLMAX, D, WARPS, MINB, SMEM, true>(a, s, ss, st)
-              : launch_stream_epi<VPLMAX, D, WARPS, MINB, SMEM, false>(a, s, ss, st);
+  const bool acc_only = a.accumulate && !a.bias && a.act == GCG_ACT_IDENTITY && !a.gate && a.n_owner == 0;
+  if (lean) return launch_stream_epi<VPLMAX, D, WARPS, MINB, SMEM, 1>(a, s, ss, st);
+  if (acc_only) return launch_stream_epi<VPLMAX, D, WARPS, MINB, SMEM, 2>(a, s, ss, st);
+  return launch_stream_epi<VPLMAX, D, WARPS, MINB, SMEM, 0>(a, s, ss, st);
 }
 
 // (VPLMAX, variant) -> kernel.  Variant 0 picks the measured default of the width class.

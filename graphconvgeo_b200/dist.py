@@ -581,8 +581,13 @@ class DistMLPCONV(MLPCONV):
     def _backward(self, G, works=None):
         def reduce_grads(ly):
             if works is not None:
-                for g in ly.grads.values():
+                for k, g in ly.grads.items():
+                    if k == "W" and getattr(ly, "_grad_reduce", None) is not None:
+                        continue          # already summed piece by piece inside the X^T.dZ1 product
                     works.append(dist.all_reduce(g, group=self.group, async_op=True))
+        # dW1 = X^T.dZ1 is the largest message of the epoch (V x h floats) and the last gradient to be computed:
+        # its pieces are all-reduced as they are finished, overlapped with the rest of the product
+        self.l_hid1._grad_reduce = (lambda t: dist.all_reduce(t, group=self.group, async_op=True)) if works is not None else None
         from .mlpconv import DropoutLayer
         grad, preact = G, False
         for i in range(len(self.layers) - 1, -1, -1):

@@ -242,21 +242,60 @@ class DenseLayer(Layer):
         return g
 
 
+def _is_big(X, F):
+    return X.nnz >= (1 << 24) and X.shape[0] * F * 4 > (256 << 20)
+
+
+def _head_split(layer, X, F):
+    """sparse.HeadSplit of a Twitter-scale X (None for small inputs or GCG_X_HEAD=0): the most frequent terms as
+    a dense block for the tensor cores, the rest as CSR.  Built once and kept on the layer."""
+    import os
+    from .sparse import HeadSplit
+    k = int(os.environ.get("GCG_X_HEAD", "256"))
+    if k <= 0 or not _is_big(X, F) or not ops.gemm_uses_tensor_cores(X.shape[0], F, k):
+        return None
+    hs = getattr(layer, "_x_head", None)
+    if hs is None or hs[0] != (id(X), k):
+        hs = ((id(X), k), HeadSplit(X, k_head=k))
+        layer._x_head = hs
+    return hs[1]
+
+
+def _x_product(layer, X, W, out, bias=None, act="identity"):
+    """act(X.W + b) (S.dot of lasagne_layers.py:26,65): one SpMM, or dense head GEMM + sparse tail at Twitter scale."""
+    hs = _head_split(layer, X, W.shape[1])
+    if hs is None:
+        return ops.spmm(X, W, bias=bias, act=act, out=out)
+    return hs.product(W, out, bias=bias, act=act)
+
+
 def _xt_product(layer, X, dZ, out):
     """dW = X^T.dZ (Dot.grad of lasagne_layers.py:26,65).  For large X the frequent terms are processed one
-    document block at a time (sparse.BlockedRows) so that the gathered rows of dZ stay in L2."""
+    document block at a time (sparse.BlockedRows) so that the gathered rows of dZ stay in L2, and the most
+    frequent ones of all as a dense tensor-core product (sparse.HeadSplit)."""
     import os
     from .sparse import BlockedRows
-    mb = int(os.environ.get("GCG_XT_BLOCK_MB", "64"))      # B200 sweep: 16 MB slower than unblocked, 64 MB best (profiles/r01_spmm_notes.md)
-    big = X.nnz >= (1 << 24) and X.shape[0] * dZ.shape[1] * 4 > (256 << 20)
-    if mb <= 0 or not big:
-        return ops.spmm(X.T, dZ, out=out)
-    key = (id(X), dZ.shape[1], mb)
-    br = getattr(layer, "_xt_blocked", None)
-    if br is None or br[0] != key:
-        br = (key, BlockedRows(X.T, dZ.shape[1], block_mb=mb))
-        layer._xt_blocked = br
-    return br[1].product(dZ, out)
+    # B200 sweeps (profiles/r01_spmm_notes.md, profiles/r02_xt_sweep.jsonl): document blocks of 96 MB of dZ rows and
+    # "heavy" = at least 16 non-zeros per block are the fastest pair at Twitter-World shape (39.0 ms vs 43.8 ms at 64 / 4)
+    mb = int(os.environ.get("GCG_XT_BLOCK_MB", "96"))
+    hf = int(os.environ.get("GCG_XT_HEAVY_FACTOR", "16"))
+    hs = _head_split(layer, X, dZ.shape[1])
+    Xs = X if hs is None else hs.tail
+    red = getattr(layer, "_grad_reduce", None)      # multi-GPU: sum the pieces over ranks as they are finished
+    if mb <= 0 or not _is_big(X, dZ.shape[1]):
+        ops.spmm(Xs.T, dZ, out=out)
+        if red is not None:
+            red(out).wait()
+    else:
+        key = (id(X), dZ.shape[1], mb, hf)
+        br = getattr(layer, "_xt_blocked", None)
+        if br is None or br[0] != key:
+            br = (key, BlockedRows(Xs.T, dZ.shape[1], block_mb=mb, heavy_factor=hf))
+            layer._xt_blocked = br
+        br[1].product(dZ, out, reduce=red)
+    if hs is not None:
+        hs.transpose_product_head(dZ, out, reduce=red)   # the head terms' rows are empty in the tail: plain placement
+    return out
 
 
 def _check_sparse(input):
@@ -274,8 +313,7 @@ class SparseInputDenseLayer(DenseLayer):
         self._X = X
         n = X.shape[0]
         fused_act = "identity" if self.nonlinearity == "softmax" else self.nonlinearity
-        out = ops.spmm(X, self.W, bias=self.b, act=fused_act,
-                       out=self._mat(("out", n), n, self.num_units))         # :26-29
+        out = _x_product(self, X, self.W, self._mat(("out", n), n, self.num_units), bias=self.b, act=fused_act)   # :26-29
         self._out = out
         return self._softmax_or(out, kwargs)
 
@@ -376,7 +414,7 @@ class SparseConvolutionDenseLayer(_ConvBase):
         X = as_csr(input, self.device)
         self._X = X
         N = X.shape[0]
-        z = ops.spmm(X, self.W, out=self._operand("Z", N, self.num_units))  # :65
+        z = _x_product(self, X, self.W, self._operand("Z", N, self.num_units))  # :65
         out = ops.spmm(self.H, z, bias=self.b, act=self.nonlinearity,
                        out=self._mat("out", N, self.num_units))             # :67-71 (bias+act fused)
         self._out = out
@@ -420,6 +458,7 @@ class ConvolutionDenseLayer(_ConvBase):
         self._s_q = self._split(("q", n_out), q, self.num_units)
         fused_act = "identity" if self.nonlinearity == "softmax" else self.nonlinearity
         out = ops.gemm(q, self.W, bias=self.b, act=fused_act, a_split=self._s_q,
+                       chained=(self.nonlinearity == "softmax"),                          # logits cancel: short chains
                        out=self._mat(("out", n_out), n_out, self.num_units))               # (.).W + b
         self._out = out
         if self.nonlinearity == "softmax" and not kwargs.get("logits", False):
@@ -461,7 +500,8 @@ class ConvolutionDenseLayer(_ConvBase):
         if self.propagate_first:
             return self._forward_propagate_first(input, ti, kwargs)
         self._s_in = self._split("in", input, self.num_units)
-        z = ops.gemm(input, self.W, out=self._operand("Z", N, self.num_units), a_split=self._s_in)   # :82
+        z = ops.gemm(input, self.W, out=self._operand("Z", N, self.num_units), a_split=self._s_in,
+                     chained=(self.nonlinearity == "softmax"))                              # :82
         Hm = self.H if ti is None else ti.Hsub
         n_out = N if ti is None else ti.n
         fused_act = "identity" if self.nonlinearity == "softmax" else self.nonlinearity

@@ -302,6 +302,10 @@ class MLPCONV:
             self.f_train()                                                 # :295
             if n % report_k_epoch == 0:
                 l_train, acc_train = self.train_results()
+                if not np.isfinite(l_train):
+                    # the reference has a NaN detector only in its MDN scripts (lang2loc_mdnshared.py:187-199);
+                    # here a non-finite loss stops the fit instead of training on garbage for n_epochs
+                    raise FloatingPointError("training loss is %r at epoch %d" % (l_train, n))
                 l_val, acc_val = self.f_val(self.y_dev_dev, self.ti["dev"])   # :297
                 if l_val < best_val_loss:
                     best_val_loss = l_val

@@ -44,6 +44,27 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+# GCG_NVTX=1: every libgcg call below is wrapped in an NVTX range named after the reference operation it replaces
+# (visible in nsys / ncu --nvtx); off by default (two extra host calls per launch)
+_NVTX = os.environ.get("GCG_NVTX") == "1"
+
+
+def _nvtx(name):
+    def deco(fn):
+        if not _NVTX:
+            return fn
+
+        def inner(*a, **k):
+            torch.cuda.nvtx.range_push(name)
+            try:
+                return fn(*a, **k)
+            finally:
+                torch.cuda.nvtx.range_pop()
+        inner.__name__, inner.__doc__ = fn.__name__, fn.__doc__
+        return inner
+    return deco
+
+
 def round_up(x, m):
     return (x + m - 1) // m * m
 
@@ -101,13 +122,14 @@ scratch = _Scratch()
 
 
 # --------------------------------------------------------------------- SpMM
-STREAM_MIN_F = int(os.environ.get("GCG_STREAM_MIN_F", 320))
+STREAM_MIN_F = int(os.environ.get("GCG_STREAM_MIN_F", 272))
 
 
 def auto_panel_cols(n_cols, F, nnz=0, prefer=None):
     """Kernel family for an SpMM the caller did not pin.  Measured on B200 (profiles/r02_spmm_stream.md), rows of
     the Twitter-World A_hat: the streaming kernel wins for wide operands gathered from HBM (F = 600: 7.7 vs 12.5
-    ms, F = 1024: 14.0 vs 22.1), ties at F = 256 and loses for narrow ones (F = 76: 3.4 vs 2.7) and for operands
+    ms, F = 1024: 14.0 vs 22.1, F = 300: 5.1 vs 10.2), ties at F = 256 / 152 and loses for narrow ones (F = 76:
+    3.4 vs 2.7) and for operands
     that sit in L2 / L1 (the document blocks of X^T.dZ1: 1.9 vs 1.0 ms), which ``prefer="gather"`` marks."""
     if _FORCE_PANEL is not None:
         return int(_FORCE_PANEL)
@@ -122,6 +144,7 @@ def auto_panel_cols(n_cols, F, nnz=0, prefer=None):
     return p
 
 
+@_nvtx("S.dot -> gcg_spmm_csr_f32")
 def spmm(A: CSRMatrix, B, out=None, bias=None, act="identity", accumulate=False, gate=None, carry=None,
          conv_out=None, panel_cols=None):
     """out = epilogue(A @ B) -- gcg_spmm_csr_f32 (S.dot, lasagne_layers.py:26,65,67,84)."""
@@ -198,12 +221,15 @@ def tf32_split(src, like=None):
 
 
 def gemm_uses_tensor_cores(M, N, K):
-    return gemm_mode_for(M, N, K) == _lib.GEMM_MODE["tf32x3"]
+    return gemm_mode_for(M, N, K) in (_lib.GEMM_MODE["tf32x3"], _lib.GEMM_MODE["tf32x3_chained"])
 
 
+@_nvtx("T.dot -> gcg_gemm_f32")
 def gemm(A, B, out=None, transA=False, transB=False, beta=0.0, bias=None, act="identity", mask=None,
-         mask_act="identity", mode=None, split_k=0, a_split=None, b_split=None):
-    """out = act(op(A) @ op(B) + beta*out + bias) [* act'(mask)] -- gcg_gemm_f32 (T.dot, lasagne_layers.py:82)."""
+         mask_act="identity", mode=None, split_k=0, a_split=None, b_split=None, chained=False):
+    """out = act(op(A) @ op(B) + beta*out + bias) [* act'(mask)] -- gcg_gemm_f32 (T.dot, lasagne_layers.py:82).
+    ``chained``: when the tensor-core engine runs this product, keep its accumulation chains short
+    (GCG_GEMM_TF32X3_CHAINED) -- for outputs whose terms cancel, i.e. the logits."""
     L = _lib.lib()
     ap, lda = _mat(A, "A")
     bp, ldb = _mat(B, "B")
@@ -233,10 +259,13 @@ def gemm(A, B, out=None, transA=False, transB=False, beta=0.0, bias=None, act="i
         mode = gemm_mode_for(M, N, K)
     elif isinstance(mode, str):
         mode = _lib.GEMM_MODE[mode]
+    x3 = mode in (_lib.GEMM_MODE["tf32x3"], _lib.GEMM_MODE["tf32x3_chained"])
+    if chained and mode == _lib.GEMM_MODE["tf32x3"]:
+        mode = _lib.GEMM_MODE["tf32x3_chained"]
     wbytes = L.gcg_gemm_workspace_bytes(int(transA), int(transB), M, N, K, mode, int(split_k))
     ws, wsb = scratch.get(wbytes, A.device)
     pre = [None, None, None, None]
-    if mode == _lib.GEMM_MODE["tf32x3"]:
+    if x3:
         if a_split is not None and a_split.matches(A, lda):
             pre[0], pre[1] = C.c_void_p(a_split.hi.data_ptr()), C.c_void_p(a_split.lo.data_ptr())
         if b_split is not None and b_split.matches(B, ldb):
@@ -290,6 +319,7 @@ def highway_mix(Hc, g, Hin, out=None):
     return out
 
 
+@_nvtx("highway gate backward -> gcg_highway_bwd_f32")
 def highway_bwd(dO, g, Hc, Hin, act, dP=None, dGpre=None, dHin=None):
     L = _lib.lib()
     n, F = dO.shape
@@ -304,6 +334,7 @@ def highway_bwd(dO, g, Hc, Hin, act, dP=None, dGpre=None, dHin=None):
     return dP, dGpre, dHin
 
 
+@_nvtx("softmax + categorical_crossentropy -> gcg_softmax_ce_f32")
 def softmax_ce(logits, y=None, probs=None, grad=None, ce=None, hit=None, pred=None, denom=None):
     """Output head on gathered logits -- gcg_softmax_ce_f32 (mlpconv.py:216,223,227-233,252)."""
     L = _lib.lib()

@@ -8,6 +8,7 @@ CUDA tensors (device memory plumbing only) plus the opaque ``gcg_plan``.
 from __future__ import annotations
 
 import ctypes as C
+import os as _os
 
 import numpy as np
 import torch
@@ -426,6 +427,88 @@ def smooth_features(H, X, device="cuda") -> "CSRMatrix":
     return spgemm(A, B, a_values=a_vals)
 
 
+class HeadSplit:
+    """X = [dense head | sparse tail] by vocabulary term, for X.W1 and X^T.dZ1 at Twitter scale.
+
+    Term frequencies are Zipf distributed: the ``k_head`` most frequent of 500 k terms hold ~36 % of X's
+    non-zeros (k_head = 256, measured on the Twitter-World-shaped workload), i.e. those columns form a
+    [N, 256] block that is ~15 % dense.  As a gather every one of its non-zeros pulls a 2.4 KB row of W1
+    through L2; as a dense block it is a tensor-core GEMM (tcgen05 3xTF32) that reads X_head once:
+        X.W1      = X_head . W1[top, :]  +  X_tail . W1              (GEMM + SpMM, accumulate)
+        X^T.dZ1   = rows `top`: X_head^T . dZ1 (GEMM, split-K);  all other rows: X_tail^T . dZ1 (SpMM)
+    The split is built once per fit (X is constant, mlpconv.py:169,294); index bookkeeping (frequency count,
+    masked selection of the tail entries) uses torch on the device -- one-off data preparation, not the hot
+    path.  Sums are re-associated (head first, then tail in CSR order): float32 rounding-level differences
+    from the single-pass product, inside the north_star tolerance (tests/test_gpu_layers.py)."""
+
+    def __init__(self, X: "CSRMatrix", k_head=256):
+        from . import ops
+        N, V = X.shape
+        dev = X.device
+        k_head = int(min(k_head, V))
+        cols = X.indices.to(torch.int64)
+        df = torch.bincount(cols, minlength=V)
+        top = torch.argsort(df, descending=True, stable=True)[:k_head]
+        top = torch.sort(top).values                       # ascending term id: the head keeps the column order
+        pos = torch.full((V,), -1, dtype=torch.int64, device=dev)
+        pos[top] = torch.arange(k_head, device=dev)
+        deg = (X.indptr[1:] - X.indptr[:-1]).to(torch.int64)
+        rows = torch.repeat_interleave(torch.arange(N, device=dev, dtype=torch.int64), deg)
+        hp = pos[cols]
+        in_head = hp >= 0
+        self.k_head = k_head
+        self.top = top
+        self.top_i32 = top.to(torch.int32)
+        self.head_nnz = int(in_head.sum().item())
+        self.head_fraction = self.head_nnz / max(1, X.nnz)
+        Xh = ops.alloc_mat(N, k_head, dev, zero=True)
+        Xh[rows[in_head], hp[in_head]] = X.data[in_head]
+        self.Xh = Xh
+        keep = ~in_head
+        t_deg = torch.zeros(N, dtype=torch.int64, device=dev).index_add_(0, rows[keep], torch.ones_like(rows[keep]))
+        t_ip = torch.zeros(N + 1, dtype=torch.int64, device=dev)
+        torch.cumsum(t_deg, 0, out=t_ip[1:])
+        self.tail = CSRMatrix(t_ip.to(torch.int32), X.indices[keep].contiguous(), X.data[keep].contiguous(), (N, V),
+                              long_row_threshold=X.long_row_threshold)
+        del rows, hp, in_head, keep, cols
+        self._split = None        # tf32 hi / lo copies of X_head (constant): made on first use
+        self._w_head = None
+        self._g_head = None
+
+    def head_split(self):
+        from . import ops
+        if self._split is None and ops.gemm_uses_tensor_cores(self.Xh.shape[0], 600, self.k_head):
+            self._split = ops.tf32_split(self.Xh)
+        return self._split
+
+    def product(self, W, out, bias=None, act="identity"):
+        """out = act(X . W + bias)"""
+        from . import ops
+        F = W.shape[1]
+        if self._w_head is None or self._w_head.shape != (self.k_head, F):
+            self._w_head = ops.alloc_mat(self.k_head, F, W.device)
+        ops.gather_rows(W, self.top_i32, out=self._w_head)
+        if bias is None and act in ("identity", "linear", None):
+            # no epilogue (the graph-conv layer applies bias / activation after A_hat): tail first through the lean
+            # SpMM, head added by the GEMM's beta = 1 epilogue
+            ops.spmm(self.tail, W, out=out)
+            return ops.gemm(self.Xh, self._w_head, out=out, beta=1.0, a_split=self.head_split())
+        ops.gemm(self.Xh, self._w_head, out=out, a_split=self.head_split())
+        return ops.spmm(self.tail, W, out=out, accumulate=True, bias=bias, act=act)
+
+    def transpose_product_head(self, dZ, dW, reduce=None):
+        """dW[top, :] = X_head^T . dZ (the other rows of dW come from the tail's transpose product)"""
+        from . import ops
+        F = dZ.shape[1]
+        if self._g_head is None or self._g_head.shape != (self.k_head, F):
+            self._g_head = ops.alloc_mat(self.k_head, F, dZ.device)
+        ops.gemm(self.Xh, dZ, transA=True, out=self._g_head, a_split=self.head_split())
+        if reduce is not None:
+            reduce(self._g_head).wait()
+        dW.index_copy_(0, self.top, self._g_head)
+        return dW
+
+
 class BlockedRows:
     """X^T.dZ with the frequent rows processed one column (document) block at a time.
 
@@ -486,21 +569,54 @@ class BlockedRows:
             hip = o_ip[b * (n_sel + 1):(b + 1) * (n_sel + 1)]
             blk = CSRMatrix(dev_ip[b * (n_sel + 1):(b + 1) * (n_sel + 1)], dev_ix[a:e], dev_d[a:e], (n_sel, N),
                             host=(hip, None, None), long_row_threshold=XT.long_row_threshold)
-            blk.spmm_mode = "gather"          # the block of dZ rows it gathers from is L2-resident by construction
+            # the block of dZ rows it gathers from is L2-resident by construction: register-gather kernel (L1-cached
+            # loads) unless GCG_XT_BLOCK_KERNEL=stream asks for the streaming one (accumulate-only epilogue)
+            blk.spmm_mode = _os.environ.get("GCG_XT_BLOCK_KERNEL", "gather")
             self.blocks.append(blk)
         self.heavy_dev = torch.from_numpy(self.heavy_ids.astype(np.int64)).to(self.device)
         self._tmp = None
 
-    def product(self, dZ, out):
-        """out[V, F] = X^T . dZ"""
+    def _light_chunks(self, n_chunks):
+        """row slices of ``light`` (plans over contiguous row ranges of the same CSR arrays)"""
+        key = int(n_chunks)
+        if getattr(self, "_chunks", None) is None or self._chunks[0] != key:
+            V = self.light.shape[0]
+            ip = self.light._host_arrays()[0]
+            bounds = np.linspace(0, V, key + 1).astype(np.int64)
+            parts = []
+            for a, e in zip(bounds[:-1], bounds[1:]):
+                hip = np.ascontiguousarray(ip[a:e + 1])
+                m = CSRMatrix(self.light.indptr[a:e + 1], self.light.indices, self.light.data, (int(e - a), self.light.shape[1]),
+                              host=(hip, None, None), long_row_threshold=self.light.long_row_threshold)
+                m.spmm_mode = getattr(self.light, "spmm_mode", None)
+                parts.append((int(a), int(e), m))
+            self._chunks = (key, parts)
+        return self._chunks[1]
+
+    def product(self, dZ, out, reduce=None, n_chunks=4):
+        """out[V, F] = X^T . dZ.  ``reduce(tensor)`` (multi-GPU: an asynchronous all-reduce that returns a handle
+        with ``wait()``) is applied to every finished piece as soon as it is computed -- the light rows in
+        ``n_chunks`` row ranges, then the compact heavy-row buffer -- so that the summation over ranks of the
+        largest gradient of the model overlaps the rest of this product instead of following it."""
         from . import ops
-        ops.spmm(self.light, dZ, out=out)
-        if not self.blocks:
-            return out
-        F = dZ.shape[1]
-        if self._tmp is None or self._tmp.shape != (self.n_heavy, F):
-            self._tmp = ops.alloc_mat(self.n_heavy, F, dZ.device)
-        for i, blk in enumerate(self.blocks):
-            ops.spmm(blk, dZ, out=self._tmp, accumulate=(i > 0))
-        out.index_copy_(0, self.heavy_dev, self._tmp)      # heavy rows are empty in `light`: plain placement
+        pending = []
+        if reduce is None:
+            ops.spmm(self.light, dZ, out=out)
+        else:
+            for a, e, part in self._light_chunks(n_chunks):
+                if e > a:
+                    ops.spmm(part, dZ, out=out[a:e])
+                    pending.append(reduce(out[a:e]))
+        if self.blocks:
+            F = dZ.shape[1]
+            if self._tmp is None or self._tmp.shape != (self.n_heavy, F):
+                self._tmp = ops.alloc_mat(self.n_heavy, F, dZ.device)
+            for i, blk in enumerate(self.blocks):
+                ops.spmm(blk, dZ, out=self._tmp, accumulate=(i > 0))
+            if reduce is not None:
+                pending.append(reduce(self._tmp))
+        for w in pending:
+            w.wait()
+        if self.blocks:
+            out.index_copy_(0, self.heavy_dev, self._tmp)      # heavy rows are empty in `light`: plain placement
         return out

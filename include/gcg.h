@@ -55,7 +55,10 @@ typedef enum {
 typedef enum {
   GCG_GEMM_FMA = 0,     /* fp32 FFMA tiles                                   */
   GCG_GEMM_TF32X3 = 1,  /* tcgen05 TF32 tensor cores, 3-term split (~fp32)   */
-  GCG_GEMM_TF32 = 2     /* tcgen05 TF32 single pass (10-bit mantissa inputs) */
+  GCG_GEMM_TF32 = 2,    /* tcgen05 TF32 single pass (10-bit mantissa inputs) */
+  GCG_GEMM_TF32X3_CHAINED = 3 /* TF32X3 with accumulation chains of 4 K blocks summed in fp32 round-to-nearest:
+                           the tensor core's round-toward-zero accumulate then costs 16 instead of 75 truncations
+                           at K = 600 -- for outputs that cancel (the logits); a few % slower */
 } gcg_gemm_mode;
 
 typedef struct gcg_plan gcg_plan; /* opaque: one per sparse matrix */
@@ -270,6 +273,8 @@ int gcg_push_rows_f32(const float* src, const int64_t* h_row_off, int32_t P, int
 /* SpMM tuning knob for experiments (scripts/spmm_sweep.py): u = gathered rows in flight per lane group,
  * minb = __launch_bounds__ min blocks (0 = compiler's choice); (0, 0) restores the defaults. */
 void gcg_spmm_set_tuning(int u, int minb);
+/* experiment knob of the register-gather kernel: lanes per output row x float4 per lane (0, 0 = automatic) */
+void gcg_spmm_set_group(int lanes, int vpl);
 
 /* ---------------------------------------------------------------- optimiser */
 

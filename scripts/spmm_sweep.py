@@ -19,19 +19,20 @@ from graphconvgeo_b200.sparse import CSRMatrix, _np_ptr  # noqa: E402
 
 
 def build_graph(n, deg, kind, dev, seed=77, comm_size=2400):
+    """kinds: chunglu (no locality at all) | community (region-sized communities of ~comm_size nodes, 80 % of the
+    edges inside; ids drawn at random, so the node order carries no locality until it is reordered) |
+    community-sorted (the same communities with contiguous node ids = the graph after reordering by region)."""
+    from graphconvgeo_b200.sparse import build_ahat_device
     gen = torch.Generator(device=dev).manual_seed(seed)
     city = None
     if kind.startswith("community"):
-        # communities of ~comm_size nodes; ids drawn at random so the node order carries no locality
         k = max(1, n // comm_size)
-        city = torch.randint(0, k, (n,), generator=gen, device=dev)
+        if kind == "community-sorted":
+            city = torch.arange(n, device=dev) // comm_size
+        else:
+            city = torch.randint(0, k, (n,), generator=gen, device=dev)
     ip, ix = synth._torch_graph(n, deg, gen, dev, city=city)
-    hip, hix = ip.cpu().numpy(), ix.cpu().numpy()
-    L = _lib.lib()
-    nnz = L.gcg_ahat_nnz_host(n, _np_ptr(hip), _np_ptr(hix))
-    oip, oix, ov = np.empty(n + 1, np.int32), np.empty(nnz, np.int32), np.empty(nnz, np.float32)
-    _lib.check(L.gcg_ahat_build_host(n, _np_ptr(hip), _np_ptr(hix), None, _np_ptr(oip), _np_ptr(oix), _np_ptr(ov)), "ahat")
-    A = CSRMatrix.from_host((oip, oix, ov), (n, n), dev)
+    A = build_ahat_device(ip, ix, n)          # the product's device builder (bit-identical to the host one)
     return A, (city.cpu().numpy() if city is not None else None)
 
 
@@ -85,7 +86,7 @@ def main():
                     A.long_row_threshold = args.thr
                     info = A.plan_info()
                     for F in args.F:
-                        if 2 * n * F * 4 > 60e9:
+                        if 2 * n * F * 4 > 100e9:
                             continue
                         B = torch.randn(n, F, device=dev)
                         Bm = ops.alloc_mat(n, F, dev)
@@ -97,9 +98,12 @@ def main():
                           for tune in args.tune:
                             tu, tm = (int(x) for x in tune.split(","))
                             _lib.lib().gcg_spmm_set_tuning(tu, tm)
-                            mean, mn = timeit(lambda: ops.spmm(A, Bm, out=out, panel_cols=panel))
+                            pc = None if panel == -9 else panel          # -9: ops.spmm's own choice of kernel
+                            mean, mn = timeit(lambda: ops.spmm(A, Bm, out=out, panel_cols=pc))
                             _lib.lib().gcg_spmm_set_tuning(0, 0)
                             print(json.dumps({"tune": tune, "n": n, "deg": deg, "graph": kind, "reorder": ro, "F": F, "panel": panel,
+                                              "kernel": {-9: "auto:" + ("stream" if ops.auto_panel_cols(n, F, A.nnz) == -2 else "gather"),
+                                                         -2: "stream", -1: "bulk-copy", 0: "gather"}.get(panel, "gather panel %d" % panel),
                                               "nnz": A.nnz, "max_deg": info["max_degree"], "n_long": info["n_long_rows"],
                                               "ms": round(mean, 4), "ms_min": round(mn, 4),
                                               "alg_GBps": round(alg / mean / 1e6, 1), "frac_of_measured_peak": round(alg / mean / 1e6 / peak, 4),

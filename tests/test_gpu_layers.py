@@ -194,3 +194,38 @@ def test_device_ahat_builder_is_bit_identical_to_host_and_oracle(n, deg, seed):
     assert np.array_equal(got.indices.cpu().numpy(), ref.indices)
     assert np.array_equal(got.data.cpu().numpy(), ref.data)
     assert np.array_equal(host.data, ref.data)
+
+
+@pytest.mark.parametrize("k_head,engine", [(32, "fma"), (64, "tf32x3")])
+def test_head_split_products_match_single_pass(k_head, engine):
+    """sparse.HeadSplit (dense block of the most frequent terms on the GEMM engine + sparse tail) against the
+    single-pass scipy products X.W and X^T.dZ: same values up to float32 re-association, north_star bound."""
+    import scipy.sparse as sp
+    from graphconvgeo_b200 import ops, synth
+    from graphconvgeo_b200.sparse import CSRMatrix, HeadSplit
+    rng = np.random.RandomState(12)
+    n, V, F = 3000, 2000, 72
+    X = synth.tfidf_matrix(n, V, 40, seed=3)
+    Xd = CSRMatrix.from_scipy(X)
+    hs = HeadSplit(Xd, k_head=k_head)
+    assert 0.1 < hs.head_fraction < 0.9 and hs.tail.nnz + hs.head_nnz == X.nnz
+    # the split is a partition of X
+    rebuilt = hs.tail.to_scipy().toarray()
+    rebuilt[:, hs.top.cpu().numpy()] += hs.Xh.cpu().numpy()
+    assert np.array_equal(rebuilt, X.toarray())
+    W = (rng.standard_normal((V, F)) * 0.1).astype(np.float32)
+    b = (rng.standard_normal(F) * 0.1).astype(np.float32)
+    dZ = rng.standard_normal((n, F)).astype(np.float32)
+    ops.set_gemm_mode(engine)
+    try:
+        out = ops.alloc_mat(n, F, "cuda")
+        hs.product(to_dev(W), out)
+        assert_close(out.cpu().numpy(), np.asarray(X @ W, dtype=np.float32), what="X.W")
+        hs.product(to_dev(W), out, bias=to_dev(b), act="tanh")
+        assert_close(out.cpu().numpy(), np.tanh(np.asarray(X @ W, dtype=np.float32) + b), what="tanh(X.W+b)")
+        dW = torch.zeros(V, F, device="cuda")
+        ops.spmm(hs.tail.T, to_dev(dZ), out=dW)
+        hs.transpose_product_head(to_dev(dZ), dW)
+        assert_close(dW.cpu().numpy(), np.asarray(sp.csr_matrix(X.T) @ dZ, dtype=np.float32), atol=2e-5, what="X^T.dZ")
+    finally:
+        ops.set_gemm_mode("auto")
