@@ -335,7 +335,7 @@ def run_gpu(args):
     dev = torch.device("cuda", local)
     if world > 1:
         import datetime
-        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=90))
 
     t0 = time.time()
     wl = synth.make_workload_device(args.workload, device=dev, seed=77, community=not args.random_graph)

@@ -75,6 +75,31 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* ba
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
+// multicast flavours for 2-CTA clusters: the TMA write lands at the same shared-memory offset (and signals the
+// mbarrier at the same offset) in every CTA of `mask`; the commit arrives on the barrier of every CTA of `mask`
+__device__ __forceinline__ void tma_load_2d_mc(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_nctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -161,7 +186,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int total_tiles = a.m_tiles * a.n_tiles * a.splits;
+  // Clusters of CS = 2 CTAs work on two M tiles of the SAME N tile and K range: each CTA loads its own A tile and
+  // HALF of the B (weight) tile, multicast into both CTAs' rings.  The kernel is bound by L2 -> SM operand traffic
+  // (64 KB per K block per CTA for 768 MMA cycles; measured 150-180 TFLOP/s effective = the L2 cap, not the tensor
+  // pipe): sharing B cuts it to 48 KB.  CS = 1 (plain launch) degenerates to the single-CTA schedule.
+  const int cs = (int)cluster_nctarank();
+  const int crank = (int)cluster_ctarank();
+  const uint16_t cmask = (uint16_t)((1u << cs) - 1u);
+  const int m_groups = (a.m_tiles + cs - 1) / cs;
+  const int total_tiles = m_groups * a.n_tiles * a.splits;          // tile GROUPS (one tile per CTA of the cluster)
+  const int tile0 = blockIdx.x / cs, tile_step = gridDim.x / cs;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmAh) : "memory");
@@ -172,7 +206,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
     }
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+    for (int s = 0; s < stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, cs); }   // slot free = every CTA's MMAs retired
     for (int s = 0; s < ACC_STAGES; ++s) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -182,6 +216,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (cs > 1) cluster_sync_all();            // the peer's barriers are initialised before anything signals them
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
 
@@ -190,9 +225,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const int nt = t % a.n_tiles, mt = (t / a.n_tiles) % a.m_tiles, z = t / (a.n_tiles * a.m_tiles);
-        const int m0 = mt * TM, n0 = nt * TN;
+      for (int t = tile0; t < total_tiles; t += tile_step) {
+        const int nt = t % a.n_tiles, mt = ((t / a.n_tiles) % m_groups) * cs + crank, z = t / (a.n_tiles * m_groups);
+        const int m0 = mt * TM, n0 = nt * TN;     // mt may be one past the last M tile (odd count): TMA zero-fills
         const int kb0 = z * a.kb_per_split, kb1 = min(a.num_kb_total, kb0 + a.kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty + stage, phase ^ 1);
@@ -210,14 +245,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
               if (a.x3) tma_load_2d(&tmAl, full + stage, sA + TILE_BYTES + j * 4096, m0 + 32 * j, k0);
             }
           }
-          if (!B_MN) {
-            tma_load_2d(&tmBh, full + stage, sB, k0, n0);                       // box {32 K, 128 N}
-            if (a.x3) tma_load_2d(&tmBl, full + stage, sB + TILE_BYTES, k0, n0);
-          } else {
+          if (cs == 1) {
+            if (!B_MN) {
+              tma_load_2d(&tmBh, full + stage, sB, k0, n0);                       // box {32 K, 128 N}
+              if (a.x3) tma_load_2d(&tmBl, full + stage, sB + TILE_BYTES, k0, n0);
+            } else {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              tma_load_2d(&tmBh, full + stage, sB + j * 4096, n0 + 32 * j, k0);
-              if (a.x3) tma_load_2d(&tmBl, full + stage, sB + TILE_BYTES + j * 4096, n0 + 32 * j, k0);
+              for (int j = 0; j < 4; ++j) {
+                tma_load_2d(&tmBh, full + stage, sB + j * 4096, n0 + 32 * j, k0);
+                if (a.x3) tma_load_2d(&tmBl, full + stage, sB + TILE_BYTES + j * 4096, n0 + 32 * j, k0);
+              }
+            }
+          } else {
+            // this CTA's half of the B tile (N rows [64*crank, 64*crank + 64)), delivered to both CTAs
+            if (!B_MN) {
+              const int hoff = crank * (TILE_BYTES / 2);                        // box {32 K, 64 N}: 8 KB
+              tma_load_2d_mc(&tmBh, full + stage, sB + hoff, k0, n0 + 64 * crank, cmask);
+              if (a.x3) tma_load_2d_mc(&tmBl, full + stage, sB + TILE_BYTES + hoff, k0, n0 + 64 * crank, cmask);
+            } else {
+#pragma unroll
+              for (int jj = 0; jj < 2; ++jj) {
+                const int j = 2 * crank + jj;
+                tma_load_2d_mc(&tmBh, full + stage, sB + j * 4096, n0 + 32 * j, k0, cmask);
+                if (a.x3) tma_load_2d_mc(&tmBl, full + stage, sB + TILE_BYTES + j * 4096, n0 + 32 * j, k0, cmask);
+              }
             }
           }
           if (++stage == stages) { stage = 0; phase ^= 1; }
@@ -234,8 +285,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
                              ((A_MN ? 1u : 0u) << 16) | ((uint32_t)(TM >> 3) << 17) | ((uint32_t)(TN >> 4) << 24);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const int z = t / (a.n_tiles * a.m_tiles);
+      for (int t = tile0; t < total_tiles; t += tile_step) {
+        const int z = t / (a.n_tiles * m_groups);
         const int kb0 = z * a.kb_per_split, kb1 = min(a.num_kb_total, kb0 + a.kb_per_split);
         const int chunk = (a.chunk_kb > 0) ? a.chunk_kb : (kb1 - kb0);
         mbar_wait(acc_empty + acc, acc_phase ^ 1);
@@ -278,7 +329,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
               umma_tf32(d_tmem, bh, ah, idesc, first);
             }
           }
-          umma_commit(empty + stage);                    // frees the ring slot when the MMAs retire
+          if (cs == 1) umma_commit(empty + stage);       // frees the ring slot when the MMAs retire
+          else umma_commit_mc(empty + stage, cmask);     // ... in both CTAs: the peer's multicast writes into it too
           if (++stage == stages) { stage = 0; phase ^= 1; }
         }
         umma_commit(acc_full + acc);                     // accumulator complete -> epilogue
@@ -295,8 +347,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
     const int ew = warp & 3;                             // TMEM lane quarter owned by this warp
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-      const int nt = t % a.n_tiles, mt = (t / a.n_tiles) % a.m_tiles, z = t / (a.n_tiles * a.m_tiles);
+    for (int t = tile0; t < total_tiles; t += tile_step) {
+      const int nt = t % a.n_tiles, mt = ((t / a.n_tiles) % m_groups) * cs + crank, z = t / (a.n_tiles * m_groups);
       const int64_t n = (int64_t)nt * TN + ew * 32 + lane;
       const int64_t m0 = (int64_t)mt * TM;
       const bool n_ok = n < g.N;
@@ -459,6 +511,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (cs > 1) cluster_sync_all();            // no CTA leaves while its peer may still multicast into it
   if (warp == 2) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
@@ -623,8 +676,17 @@ int gemm_tc_launch(const GemmArgs& g0, int transA, int transB, int mode, void* w
       Bl = const_cast<float*>(g.B_lo);
     }
   }
+  // 2-CTA clusters share the B tile by multicast (see the kernel): worth it when there are enough M tiles to pair up
+  // MEASURED (B200, profiles/r02_gemm_notes.md): the clustered schedule is bit-identical but SLOWER (3xTF32 140 vs
+  // 148 TFLOP/s at 450k x 600 x 600, plain TF32 279 vs 343): the two CTAs advance in lockstep through a 3-stage ring
+  // and stall on each other's slot releases, which costs more than the halved B traffic saves.  Default: off.
+  const int cluster_env = getenv("GCG_GEMM_CLUSTER") ? atoi(getenv("GCG_GEMM_CLUSTER")) : 1;          // read per call:
+  const int cluster_min = getenv("GCG_GEMM_CLUSTER_MIN_TILES") ? atoi(getenv("GCG_GEMM_CLUSTER_MIN_TILES")) : 64;   // tests flip them
+  const int64_t m_tiles64 = ceil_div(g.M, TM);
+  const int cs = (cluster_env >= 2 && m_tiles64 >= cluster_min) ? 2 : 1;
   CUtensorMap mAh, mAl, mBh, mBl;
-  const int a_box = transA ? 32 : TM, b_box = transB ? TN : 32;   // MN-major operands load {32 MN, 32 K} boxes
+  // MN-major operands load {32 MN, 32 K} boxes; a clustered K-major B is loaded in two {32 K, 64 N} halves
+  const int a_box = transA ? 32 : TM, b_box = transB ? (cs == 2 ? TN / 2 : TN) : 32;
   const bool a_mn = transA != 0, b_mn = transB == 0;
   bool ok = make_map(&mAh, Ah, a_rows, a_cols, g.lda, a_box, a_mn) && make_map(&mBh, Bh, b_rows, b_cols, g.ldb, b_box, b_mn);
   if (x3) ok = ok && make_map(&mAl, Al, a_rows, a_cols, g.lda, a_box, a_mn) && make_map(&mBl, Bl, b_rows, b_cols, g.ldb, b_box, b_mn);
@@ -645,19 +707,34 @@ int gemm_tc_launch(const GemmArgs& g0, int transA, int transB, int mode, void* w
   // instead of 75 at K = 600 (measured at Twitter-World: logits error 2.1x -> 1.0x -> below the 1e-4 bound)
   // measured in the Twitter-World epoch: chains of 4 K blocks everywhere cost +15 ms of 55 ms of GEMMs (the epilogue
   // warps drain TMEM once per chain), so only callers that ask for it (GCG_GEMM_TF32X3_CHAINED) get short chains
-  static const int chunk_env = getenv("GCG_GEMM_CHUNK_KB") ? atoi(getenv("GCG_GEMM_CHUNK_KB")) : 0;
+  const int chunk_env = getenv("GCG_GEMM_CHUNK_KB") ? atoi(getenv("GCG_GEMM_CHUNK_KB")) : 0;
   const int chunk = (mode == GCG_GEMM_TF32X3_CHAINED) ? 4 : chunk_env;
   ta.chunk_kb = (x3 && chunk > 0 && kbps > chunk) ? chunk : 0;
-  const int64_t total = (int64_t)ta.m_tiles * ta.n_tiles * split;
-  if (total >= INT32_MAX) return GCG_ERR_UNSUPPORTED;
+  const int64_t total = ceil_div(ta.m_tiles, cs) * ta.n_tiles * split;        // tile groups (one tile per CTA of a cluster)
+  if (total * cs >= INT32_MAX) return GCG_ERR_UNSUPPORTED;
   const int smem_bytes = (x3 ? 3 * 4 : 6 * 2) * TILE_BYTES + 1024 + 256;
-  const unsigned grid = (unsigned)std::min<int64_t>(total, kNumSMs);
+  const unsigned grid = (unsigned)(std::min<int64_t>(total, kNumSMs / cs) * cs);
   // A is MN-major when it is stored [K][M] (transA); B is MN-major when stored [K][N] (!transB)
   auto launch = [&](auto kern) -> cudaError_t {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e != cudaSuccess) return e;
-    kern<<<grid, TC_THREADS, smem_bytes, st>>>(mAh, mAl, mBh, mBl, ta);
-    return cudaGetLastError();
+    if (cs == 1) {
+      kern<<<grid, TC_THREADS, smem_bytes, st>>>(mAh, mAl, mBh, mBl, ta);
+      return cudaGetLastError();
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid, 1, 1);
+    cfg.blockDim = dim3(TC_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = (size_t)smem_bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cs;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, mAh, mAl, mBh, mBl, ta);
   };
   cudaError_t e;
   if (!transA && !transB) e = launch(gemm_tc_kernel<false, true>);

@@ -532,10 +532,31 @@ class DistMLPCONV(MLPCONV):
         self.Xd = CSRMatrix.from_host((p, np.ascontiguousarray(ix[ip[part.r0]:ip[part.r1]]),
                                        np.ascontiguousarray(d[ip[part.r0]:ip[part.r1]])),
                                       (part.n_loc, in_size), self.device, 1024)
+        # Decisions about X's layout that shape COLLECTIVES (which terms form the dense head, which rows of X^T are
+        # heavy: their gradient blocks are summed over ranks as whole buffers) are taken once from the GLOBAL X, so
+        # every rank issues the same all-reduces on buffers of the same shape and meaning.
+        import os
+        from .sparse import BlockedRows, HeadSplit
+        from .lasagne_layers import _is_big
+        F = int(self.hidden_layer_size)
+        k_head = int(os.environ.get("GCG_X_HEAD", "256"))
+        big = _is_big(Xg, F)
+        top = None
+        if big and k_head > 0 and ops.gemm_uses_tensor_cores(part.n_loc, F, k_head):
+            top = HeadSplit.top_terms(Xg.indices, in_size, k_head)
+        heavy_ids = None
+        if big:
+            df = torch.bincount(Xg.indices.to(torch.int64), minlength=in_size)
+            if top is not None:
+                df[top] = 0                                   # the head terms leave the sparse part
+            heavy_ids = BlockedRows.heavy_rows(df.cpu().numpy(), n, F, float(os.environ.get("GCG_XT_BLOCK_MB", "96")),
+                                               int(os.environ.get("GCG_XT_HEAVY_FACTOR", "16")))
+        self._x_plan = dict(big=big, top=top, heavy_ids=heavy_ids)
         if getattr(self, "keep_host_inputs", False):      # for checkers (host_inputs): the global matrices, model order
             self._host_inputs = (Xg.to_scipy(), Hg.to_scipy())
         del Xg, Hg
         self._build(self.Xd, Hd, in_size, out_size)
+        self.l_hid1._x_plan = self._x_plan
         self.ti = {}
         self._sel = {}
         for name, idx in (("train", train_indices), ("dev", dev_indices), ("test", test_indices)):

@@ -243,6 +243,9 @@ class DenseLayer(Layer):
 
 
 def _is_big(X, F):
+    import os
+    if os.environ.get("GCG_X_FORCE_BIG") == "1":      # tests: exercise the Twitter-scale code paths on small inputs
+        return True
     return X.nnz >= (1 << 24) and X.shape[0] * F * 4 > (256 << 20)
 
 
@@ -252,11 +255,15 @@ def _head_split(layer, X, F):
     import os
     from .sparse import HeadSplit
     k = int(os.environ.get("GCG_X_HEAD", "256"))
-    if k <= 0 or not _is_big(X, F) or not ops.gemm_uses_tensor_cores(X.shape[0], F, k):
+    plan = getattr(layer, "_x_plan", None)         # multi-GPU: decisions taken once from the GLOBAL X (dist.py)
+    if plan is not None:
+        if plan.get("top") is None:
+            return None
+    elif k <= 0 or not _is_big(X, F) or not ops.gemm_uses_tensor_cores(X.shape[0], F, k):
         return None
     hs = getattr(layer, "_x_head", None)
     if hs is None or hs[0] != (id(X), k):
-        hs = ((id(X), k), HeadSplit(X, k_head=k))
+        hs = ((id(X), k), HeadSplit(X, k_head=k, top=None if plan is None else plan["top"]))
         layer._x_head = hs
     return hs[1]
 
@@ -277,12 +284,14 @@ def _xt_product(layer, X, dZ, out):
     from .sparse import BlockedRows
     # B200 sweeps (profiles/r01_spmm_notes.md, profiles/r02_xt_sweep.jsonl): document blocks of 96 MB of dZ rows and
     # "heavy" = at least 16 non-zeros per block are the fastest pair at Twitter-World shape (39.0 ms vs 43.8 ms at 64 / 4)
-    mb = int(os.environ.get("GCG_XT_BLOCK_MB", "96"))
+    mb = float(os.environ.get("GCG_XT_BLOCK_MB", "96"))
     hf = int(os.environ.get("GCG_XT_HEAVY_FACTOR", "16"))
     hs = _head_split(layer, X, dZ.shape[1])
     Xs = X if hs is None else hs.tail
     red = getattr(layer, "_grad_reduce", None)      # multi-GPU: sum the pieces over ranks as they are finished
-    if mb <= 0 or not _is_big(X, dZ.shape[1]):
+    plan = getattr(layer, "_x_plan", None)          # multi-GPU: the same blocking decisions on every rank
+    big = _is_big(X, dZ.shape[1]) if plan is None else plan["big"]
+    if mb <= 0 or not big:
         ops.spmm(Xs.T, dZ, out=out)
         if red is not None:
             red(out).wait()
@@ -290,7 +299,8 @@ def _xt_product(layer, X, dZ, out):
         key = (id(X), dZ.shape[1], mb, hf)
         br = getattr(layer, "_xt_blocked", None)
         if br is None or br[0] != key:
-            br = (key, BlockedRows(Xs.T, dZ.shape[1], block_mb=mb, heavy_factor=hf))
+            br = (key, BlockedRows(Xs.T, dZ.shape[1], block_mb=mb, heavy_factor=hf,
+                                   heavy_ids=None if plan is None else plan["heavy_ids"]))
             layer._xt_blocked = br
         br[1].product(dZ, out, reduce=red)
     if hs is not None:

@@ -427,6 +427,10 @@ def smooth_features(H, X, device="cuda") -> "CSRMatrix":
     return spgemm(A, B, a_values=a_vals)
 
 
+def _min_block_cols():
+    return int(_os.environ.get("GCG_XT_BLOCK_MIN_COLS", "1024"))     # tests lower it to block small inputs
+
+
 class HeadSplit:
     """X = [dense head | sparse tail] by vocabulary term, for X.W1 and X^T.dZ1 at Twitter scale.
 
@@ -441,15 +445,24 @@ class HeadSplit:
     path.  Sums are re-associated (head first, then tail in CSR order): float32 rounding-level differences
     from the single-pass product, inside the north_star tolerance (tests/test_gpu_layers.py)."""
 
-    def __init__(self, X: "CSRMatrix", k_head=256):
+    @staticmethod
+    def top_terms(indices, V, k_head):
+        """ids of the ``k_head`` most frequent columns (ascending id; ties -> lower id), as an int64 device tensor"""
+        df = torch.bincount(indices.to(torch.int64), minlength=V)
+        top = torch.argsort(df, descending=True, stable=True)[:int(min(k_head, V))]
+        return torch.sort(top).values
+
+    def __init__(self, X: "CSRMatrix", k_head=256, top=None):
+        """``top``: the head's term ids when they are decided elsewhere -- in multi-GPU runs every rank must use the
+        SAME terms (chosen from the global X), because the head rows of dW1 are summed over ranks as one block."""
         from . import ops
         N, V = X.shape
         dev = X.device
-        k_head = int(min(k_head, V))
         cols = X.indices.to(torch.int64)
-        df = torch.bincount(cols, minlength=V)
-        top = torch.argsort(df, descending=True, stable=True)[:k_head]
-        top = torch.sort(top).values                       # ascending term id: the head keeps the column order
+        if top is None:
+            top = self.top_terms(X.indices, V, k_head)     # ascending term id: the head keeps the column order
+        top = top.to(device=dev, dtype=torch.int64)
+        k_head = int(top.numel())
         pos = torch.full((V,), -1, dtype=torch.int64, device=dev)
         pos[top] = torch.arange(k_head, device=dev)
         deg = (X.indptr[1:] - X.indptr[:-1]).to(torch.int64)
@@ -519,21 +532,34 @@ class BlockedRows:
     into a compact [n_heavy, F] buffer (empty (row, block) pairs are skipped by the kernel).  The light
     rows are done in one ordinary pass.  Result identical up to summation order inside the heavy rows."""
 
-    def __init__(self, XT: CSRMatrix, F, block_mb=32, heavy_factor=4):
+    @staticmethod
+    def heavy_rows(row_nnz, n_cols, F, block_mb, heavy_factor):
+        """the rule that makes a row of X^T 'heavy': at least ``heavy_factor`` non-zeros per document block"""
+        block_cols = max(_min_block_cols(), int(block_mb * (1 << 20) // (4 * max(F, 1))))
+        n_blocks = int(-(-n_cols // block_cols))
+        return np.flatnonzero(np.asarray(row_nnz) >= heavy_factor * n_blocks).astype(np.int32)
+
+    def __init__(self, XT: CSRMatrix, F, block_mb=32, heavy_factor=4, heavy_ids=None):
+        """``heavy_ids``: the heavy rows when they are decided elsewhere -- in multi-GPU runs every rank must use the
+        SAME set (from the global term frequencies): the compact heavy-row buffer is summed over ranks as one block."""
         ip, ix, d = XT._host_arrays()
         V, N = XT.shape
         self.shape = XT.shape
         self.device = XT.device
-        block_cols = max(1024, int(block_mb * (1 << 20) // (4 * max(F, 1))))
+        block_cols = max(_min_block_cols(), int(block_mb * (1 << 20) // (4 * max(F, 1))))
         self.n_blocks = int(-(-N // block_cols))
         self.block_cols = block_cols
         lens = np.diff(ip)
-        heavy = lens >= heavy_factor * self.n_blocks
+        if heavy_ids is None:
+            heavy = lens >= heavy_factor * self.n_blocks
+        else:
+            heavy = np.zeros(V, bool)
+            heavy[np.asarray(heavy_ids, dtype=np.int64)] = True
         self.heavy_ids = np.flatnonzero(heavy).astype(np.int32)
         n_sel = len(self.heavy_ids)
         self.n_heavy = n_sel
         self.heavy_nnz_fraction = float(lens[heavy].sum()) / max(1, int(lens.sum()))
-        if n_sel == 0 or self.n_blocks <= 1:
+        if heavy_ids is None and (n_sel == 0 or self.n_blocks <= 1):
             self.light = XT
             self.blocks = []
             return

@@ -7,11 +7,11 @@ or the CPU comparator, never as the product path.
 
 Parity status (see DESIGN.md "Oracle"):
 
-* GCN layers / loss / backward / Adam (``gcn_oracle.py``): **parity unpinned by
-  the reference** -- the reference ships no tests, golden vectors or fixtures
-  and its own executable (Python 2 + Theano + Lasagne) cannot run in this
-  image.  The restatement follows the reference source line by line (each
-  function cites file:line) and is cross-checked against torch-CPU autograd.
+* GCN layers / loss / Adam / fit loop (``gcn_oracle.py``): **pinned** to outputs of the
+  reference's own source executed under stub theano / lasagne modules
+  (tests/golden/make_layers_golden.py: forward bodies, A_hat, geo_eval, bit for bit;
+  tests/golden/make_fit_golden.py: a whole ``MLPCONV.fit`` run).  The hand-written backward of
+  the >2-layer / gated extension is cross-checked against torch-CPU autograd.
 * Highway gate: **parity unpinned** -- the gate is not in the reference at all;
   the oracle restates the formula given in BASELINE.json's ``north_star``.
 * Input smoothing ``X_conv = H * X`` (``mlp_oracle.smooth_features``): **pinned** -- the

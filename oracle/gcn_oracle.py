@@ -6,10 +6,15 @@ The reference executes these through Theano/Lasagne on CPU; Theano's sparse
 per row, per non-zero in CSR order, ``y += a * x`` with separately rounded
 multiply and add) and ``T.dot`` to BLAS sgemm -- exactly the calls used here.
 
-Parity status: UNPINNED by the reference (it has no tests / golden vectors and
-cannot run here); cross-checked against torch-CPU autograd in
-tests/test_oracle.py.  The highway gate is not in the reference; its spec is
-the formula in BASELINE.json ``north_star`` (see ``highway_mix``).
+Parity status: the reference ships no tests / golden vectors and cannot run here as it is
+(Python 2 + Theano + Lasagne), so fixtures were produced by EXECUTING ITS SOURCE under stub
+theano / lasagne modules (scripts and outputs under tests/golden/):
+  * forward layers, A_hat builder, geo_eval: pinned bit for bit (tests/test_layers_golden.py);
+  * loss / regulariser composition, Adam, the fit loop, predict: pinned to a run of the reference's own
+    MLPCONV.fit (tests/test_fit_golden.py; tolerances of float32 summation order);
+  * hand-written backward of the >2-layer / gated extension: cross-checked against torch-CPU float64
+    autograd (tests/test_oracle.py).  The highway gate is not in the reference; its spec is the formula in
+    BASELINE.json ``north_star`` (see ``highway_mix``): parity unpinned.
 """
 from __future__ import annotations
 
@@ -404,3 +409,32 @@ def train_epochs(net, params, idx, y, n_epochs, lr=4e-3):
         adam_step(params, grads, state, lr=lr)
         hist.append((float(loss), acc))
     return hist
+
+
+def fit_loop(net, params, train_idx, y_train, dev_idx, y_dev, n_epochs, early_stopping_max_down=100000, lr=4e-3):
+    """The epoch loop of MLPCONV.fit, mlpconv.py:288-317: one f_train per epoch; every 10th epoch f_val on dev, a
+    strictly better dev loss snapshots the parameters (after that epoch's update) and resets the counter, anything
+    else increments it; stop when the counter EXCEEDS early_stopping_max_down; finally restore the best snapshot
+    and validate once more.  ``params`` is updated in place and ends as the best snapshot.
+    Returns (train history [(loss, acc)], val history [(loss, acc)] incl. the final one, best parameter list)."""
+    state = AdamState(params)
+    train_hist, val_hist = [], []
+    best, best_val_loss, n_down = None, float("inf"), 0
+    for n in range(n_epochs):
+        loss, acc, grads, _ = net.loss_and_grads(params, train_idx, y_train)       # :295 (loss before the update)
+        adam_step(params, grads, state, lr=lr)
+        train_hist.append((float(loss), acc))
+        if n % 10 == 0:                                                           # :296
+            l_val, a_val = net.loss_acc(params, dev_idx, y_dev)                   # :297
+            val_hist.append((float(l_val), a_val))
+            if l_val < best_val_loss:                                             # :298-302
+                best_val_loss, best, n_down = l_val, [p.copy() for p in params], 0
+            else:
+                n_down += 1                                                       # :305
+            if n_down > early_stopping_max_down:                                  # :307-309
+                break
+    for p, b in zip(params, best):                                                # :314
+        p[...] = b
+    l_val, a_val = net.loss_acc(params, dev_idx, y_dev)                           # :317
+    val_hist.append((float(l_val), a_val))
+    return train_hist, val_hist, best

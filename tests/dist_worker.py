@@ -26,11 +26,24 @@ def gpu_main():
     # the last case runs with drop_out=True and p = 0: the DropoutLayer sits in the chain (its branch of the
     # backward must hand the layer below a gradient w.r.t. the ACTIVATION, so relu' is applied there) while the
     # masks are the identity, so the oracle without dropout is the reference
-    for n_layers, highway, reorder, partition, peer, drop in (
+    cases = [
             (2, False, None, "row", False, False), (3, True, "labels", "row", False, False),
             (2, False, "labels", "feature", False, False), (3, True, None, "feature", False, False),
             (3, True, "labels", "feature", True, False), (2, False, None, "feature", True, False),
-            (3, True, None, "row", False, True), (2, False, "labels", "feature", True, True)):
+            (3, True, None, "row", False, True), (2, False, "labels", "feature", True, True),
+            # Twitter-scale code paths forced on the small input: dense head of X on the tensor-core engine, document-
+            # blocked X^T.dZ1, dW1 summed over ranks piece by piece (the pieces must mean the same on every rank)
+            (3, True, "labels", "feature", True, "big"), (2, False, None, "row", False, "big")]
+    for n_layers, highway, reorder, partition, peer, drop in cases:
+        big = drop == "big"
+        drop = drop is True
+        os.environ["GCG_X_FORCE_BIG"] = "1" if big else "0"
+        os.environ["GCG_X_HEAD"] = "32" if big else "256"
+        os.environ["GCG_XT_BLOCK_MB"] = "0.015" if big else "96"
+        os.environ["GCG_XT_BLOCK_MIN_COLS"] = "128" if big else "1024"
+        os.environ["GCG_XT_HEAVY_FACTOR"] = "1" if big else "16"
+        from graphconvgeo_b200 import ops as _ops
+        _ops.set_gemm_mode("tf32x3" if big else "auto")
         rng = np.random.RandomState(5)
         params = go.init_params(rng, w.X.shape[1], w.hidden, w.n_classes, n_layers, highway)
         idx = rng.choice(w.train_indices, size=len(w.train_indices)).astype(np.int32)      # duplicates
@@ -55,6 +68,10 @@ def gpu_main():
                     assert_close(m.node_rows(ly._out), c["A"][i], what="activation %d" % i)
         for p_gpu, p in zip(m.get_param_values(), ref_params):
             assert_close(p_gpu, p, atol=1e-5, rtol=1e-3, what="params after 3 steps")
+        if big:
+            l1 = m.l_hid1
+            assert getattr(l1, "_x_head", None) is not None and getattr(l1, "_xt_blocked", None) is not None
+            assert len(l1._xt_blocked[1].blocks) > 1
         from graphconvgeo_b200 import lasagne_layers as L
         L.set_all_param_values(m.l_out, ref_params)
         proba = m.predict_proba("test")
@@ -69,7 +86,7 @@ def gpu_main():
         assert abs(acc - ref_acc) <= 2.0 / len(w.test_indices)
         if rank == 0:
             print("dist case", n_layers, highway, reorder, partition, "peer" if (peer and m.part.peer is not None) else "nccl",
-                  "dropout(p=0)" if drop else "", "OK", flush=True)
+                  "dropout(p=0)" if drop else "", "forced Twitter-scale paths" if big else "", "OK", flush=True)
         if m.part.peer is not None:
             m.part.peer.check()
     dist.barrier()

@@ -145,3 +145,28 @@ def test_presplit_operands_give_identical_results():
     assert torch.equal(ops.gemm(A, B, mode="tf32x3", a_split=other), r0)
     # the FFMA engine ignores pre-split operands
     assert_close(ops.gemm(A, B, mode="fma", a_split=sA).cpu().numpy(), r0.cpu().numpy(), atol=1e-5)
+
+
+@pytest.mark.parametrize("ta,tb", [(False, False), (True, False), (False, True), (True, True)])
+@pytest.mark.parametrize("M,N,K,chained", [(1024, 600, 600, False), (1100, 256, 320, True), (640, 1024, 1000, False),
+                                           (129, 70, 64, True), (2000, 600, 8200, False)])
+def test_clustered_multicast_gemm_equals_single_cta(ta, tb, M, N, K, chained, monkeypatch):
+    """2-CTA clusters (the B tile multicast into both CTAs, odd M-tile counts, all four operand majors, chained
+    accumulation, split-K) must give the very bits of the single-CTA schedule: same MMAs in the same order."""
+    from graphconvgeo_b200 import ops
+    if "tf32x3" not in tc_modes():
+        pytest.skip("tcgen05 engine unavailable")
+    rng = np.random.RandomState(M + N + K)
+    s = 1.0 / np.sqrt(K)
+    A = to_dev((rng.standard_normal((K, M) if ta else (M, K)) * s).astype(np.float32))
+    B = to_dev(rng.standard_normal((N, K) if tb else (K, N)).astype(np.float32))
+    bias = to_dev(rng.standard_normal(N).astype(np.float32))
+    monkeypatch.setenv("GCG_GEMM_CLUSTER", "1")
+    one = ops.gemm(A, B, transA=ta, transB=tb, mode="tf32x3", bias=bias, act="rectify", chained=chained).clone()
+    monkeypatch.setenv("GCG_GEMM_CLUSTER", "2")
+    monkeypatch.setenv("GCG_GEMM_CLUSTER_MIN_TILES", "1")
+    two = ops.gemm(A, B, transA=ta, transB=tb, mode="tf32x3", bias=bias, act="rectify", chained=chained)
+    torch.cuda.synchronize()
+    assert torch.equal(one, two), (ta, tb, M, N, K, float((one - two).abs().max()))
+    ref = np.maximum(ref_gemm(A.cpu().numpy(), B.cpu().numpy(), ta, tb) + bias.cpu().numpy()[None, :], 0)
+    assert_close(two.cpu().numpy(), ref, atol=4e-5 * max(1.0, np.abs(ref).max()))
