@@ -55,6 +55,7 @@ PROTOTYPES = {
     "gcg_softmax_ce_f32": (c_int, [c_vp, c_i64, c_vp, c_i64, c_i64, c_f32, c_vp, c_i64, c_vp, c_i64, c_vp,
                                    c_vp, c_vp, c_vp]),
     "gcg_sum_f32": (c_int, [c_vp, c_i64, c_f32, c_vp, c_vp]),
+    "gcg_sum_slabs_f32": (c_int, [c_vp, c_i32, c_i64, c_vp, c_vp]),
     "gcg_scatter_rows_f32": (c_int, [c_vp, c_i64, c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp]),
     "gcg_gather_rows_f32": (c_int, [c_vp, c_i64, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp]),
     "gcg_pack_cols_f32": (c_int, [c_vp, c_i64, c_i64, c_i64, c_i32, c_i64, c_vp, c_vp]),

@@ -398,6 +398,32 @@ __global__ void __launch_bounds__(256) elastic_net_kernel(const AdamTable tb, fl
 
 using namespace gcg;
 
+// dst[i] = sum over s (ascending) of src[s * slab + i]: the per-document-block partial rows of X^T.dZ1 reduced in
+// block order (deterministic); float4 path, slab must be a multiple of 4 floats
+__global__ void __launch_bounds__(256) sum_slabs_kernel(const float4* __restrict__ src, int n_slabs, int64_t slab4,
+                                                        float4* __restrict__ dst) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < slab4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 a = src[i];
+    for (int sgi = 1; sgi < n_slabs; ++sgi) {
+      const float4 b = src[(int64_t)sgi * slab4 + i];
+      a.x = __fadd_rn(a.x, b.x); a.y = __fadd_rn(a.y, b.y); a.z = __fadd_rn(a.z, b.z); a.w = __fadd_rn(a.w, b.w);
+    }
+    dst[i] = a;
+  }
+}
+
+extern "C" int gcg_sum_slabs_f32(const float* src, int32_t n_slabs, int64_t slab_floats, float* dst, void* stream) {
+  GCG_CHECK_ARG(src && dst && n_slabs > 0 && slab_floats >= 0, "gcg_sum_slabs_f32: bad argument");
+  GCG_CHECK_SHAPE(slab_floats % 4 == 0 && aligned16(src) && aligned16(dst), "gcg_sum_slabs_f32: needs 16-byte aligned slabs of 4k floats");
+  if (slab_floats == 0) return GCG_OK;
+  const int64_t slab4 = slab_floats / 4;
+  const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(slab4, 256), (int64_t)kNumSMs * 16);
+  sum_slabs_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const float4*>(src), n_slabs, slab4,
+                                                                              reinterpret_cast<float4*>(dst));
+  GCG_LAUNCH_CHECK();
+  return GCG_OK;
+}
+
 extern "C" int64_t gcg_colsum_workspace_bytes(int64_t n_rows, int64_t F) {
   if (n_rows <= 0 || F <= 0) return 0;
   return (int64_t)colsum_parts(n_rows, F) * F * (int64_t)sizeof(float);

@@ -168,7 +168,7 @@ struct TcArgs {
   int chunk_kb;                                 // 3xTF32: K blocks per accumulation chain (0 = one chain per tile)
 };
 
-template <bool A_MN, bool B_MN>
+template <bool A_MN, bool B_MN, int CS, bool CHAINED>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
@@ -190,8 +190,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
   // HALF of the B (weight) tile, multicast into both CTAs' rings.  The kernel is bound by L2 -> SM operand traffic
   // (64 KB per K block per CTA for 768 MMA cycles; measured 150-180 TFLOP/s effective = the L2 cap, not the tensor
   // pipe): sharing B cuts it to 48 KB.  CS = 1 (plain launch) degenerates to the single-CTA schedule.
-  const int cs = (int)cluster_nctarank();
-  const int crank = (int)cluster_ctarank();
+  constexpr int cs = CS;                      // compile-time: the single-CTA kernel carries none of the cluster code
+  const int crank = (CS > 1) ? (int)cluster_ctarank() : 0;
   const uint16_t cmask = (uint16_t)((1u << cs) - 1u);
   const int m_groups = (a.m_tiles + cs - 1) / cs;
   const int total_tiles = m_groups * a.n_tiles * a.splits;          // tile GROUPS (one tile per CTA of the cluster)
@@ -288,7 +288,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
       for (int t = tile0; t < total_tiles; t += tile_step) {
         const int z = t / (a.n_tiles * m_groups);
         const int kb0 = z * a.kb_per_split, kb1 = min(a.num_kb_total, kb0 + a.kb_per_split);
-        const int chunk = (a.chunk_kb > 0) ? a.chunk_kb : (kb1 - kb0);
+        const int chunk = (CHAINED && a.chunk_kb > 0) ? a.chunk_kb : (kb1 - kb0);
         mbar_wait(acc_empty + acc, acc_phase ^ 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         uint32_t d_tmem = tmem_base + acc * 2 * TM;
@@ -359,10 +359,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
       const bool accum_like = g.act == GCG_ACT_IDENTITY && g.bias == nullptr &&
                               (g.mask == nullptr || g.mask_act == GCG_ACT_RELU || g.mask_act == GCG_ACT_TANH);
       const int kb0e = z * a.kb_per_split, kb1e = min(a.num_kb_total, kb0e + a.kb_per_split);
-      const int n_chains = (a.chunk_kb > 0) ? (kb1e - kb0e + a.chunk_kb - 1) / a.chunk_kb : 1;
+      const int n_chains = (CHAINED && a.chunk_kb > 0) ? (kb1e - kb0e + a.chunk_kb - 1) / a.chunk_kb : 1;
       mbar_wait(acc_full + acc, acc_phase);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      if (n_chains > 1) {
+      if (CHAINED && n_chains > 1) {
         // running sums of the chains in registers (fp32 round-to-nearest); the total goes back into the LAST
         // chain's TMEM stage so that the (code-size critical) store phase below stays as it is
         float sum[TM / 32][32];
@@ -737,10 +737,15 @@ int gemm_tc_launch(const GemmArgs& g0, int transA, int transB, int mode, void* w
     return cudaLaunchKernelEx(&cfg, kern, mAh, mAl, mBh, mBl, ta);
   };
   cudaError_t e;
-  if (!transA && !transB) e = launch(gemm_tc_kernel<false, true>);
-  else if (transA && !transB) e = launch(gemm_tc_kernel<true, true>);
-  else if (!transA && transB) e = launch(gemm_tc_kernel<false, false>);
-  else e = launch(gemm_tc_kernel<true, false>);
+  const bool ch = ta.chunk_kb > 0;
+#define GCG_TC(AM, BM) \
+  (cs == 1 ? (ch ? launch(gemm_tc_kernel<AM, BM, 1, true>) : launch(gemm_tc_kernel<AM, BM, 1, false>)) \
+           : (ch ? launch(gemm_tc_kernel<AM, BM, 2, true>) : launch(gemm_tc_kernel<AM, BM, 2, false>)))
+  if (!transA && !transB) e = GCG_TC(false, true);
+  else if (transA && !transB) e = GCG_TC(true, true);
+  else if (!transA && transB) e = GCG_TC(false, false);
+  else e = GCG_TC(true, false);
+#undef GCG_TC
   if (e != cudaSuccess) {
     set_error("gemm_tc_launch: %s", cudaGetErrorString(e));
     return GCG_ERR_CUDA;

@@ -358,6 +358,16 @@ def sum_scaled(x, scale=1.0, out=None):
     return out
 
 
+def sum_slabs(src, n_slabs, out):
+    """out = sum over the n_slabs equal slabs of ``src`` in slab order (gcg_sum_slabs_f32)."""
+    slab = out.numel()
+    if src.numel() != n_slabs * slab or not src.is_contiguous() or not out.is_contiguous():
+        raise ValueError("sum_slabs: src must be %d contiguous slabs of out's size" % n_slabs)
+    _lib.check(_lib.lib().gcg_sum_slabs_f32(C.c_void_p(src.data_ptr()), int(n_slabs), int(slab), C.c_void_p(out.data_ptr()),
+                                            _stream()), "gcg_sum_slabs_f32")
+    return out
+
+
 def scatter_rows(G, pos_ptr, pos_idx, n_rows, out=None):
     L = _lib.lib()
     gp, ldg = _mat(G, "G")

@@ -601,6 +601,21 @@ class BlockedRows:
             self.blocks.append(blk)
         self.heavy_dev = torch.from_numpy(self.heavy_ids.astype(np.int64)).to(self.device)
         self._tmp = None
+        # ONE matrix of all (document block, heavy row) pieces, block-major: row b*n_heavy + r holds the non-zeros of
+        # heavy row r inside document block b.  A single balanced streaming SpMM over it (its spans run block by block,
+        # so the block of dZ rows being gathered stays L2-resident) writes per-block partial rows; gcg_sum_slabs_f32
+        # adds them in block order.  Replaces n_blocks launches that each re-read and re-wrote the heavy-row buffer.
+        self.stacked = None
+        if _os.environ.get("GCG_XT_STACKED", "1") != "0" and F % 4 == 0 and (n_sel * nb) < 2 ** 31 - 2:
+            s_ip = np.empty(nb * n_sel + 1, np.int64)
+            for b in range(nb):
+                s_ip[b * n_sel:(b + 1) * n_sel] = o_ip[b * (n_sel + 1):(b + 1) * (n_sel + 1) - 1].astype(np.int64) + o_off[b]
+            s_ip[-1] = tot
+            s_ip32 = s_ip.astype(np.int32)
+            self.stacked = CSRMatrix(torch.from_numpy(s_ip32).to(self.device), dev_ix, dev_d, (nb * n_sel, N),
+                                     host=(s_ip32, None, None), long_row_threshold=XT.long_row_threshold)
+            self.stacked.spmm_mode = _os.environ.get("GCG_XT_STACKED_KERNEL", "stream")
+            self._partial = None
 
     def _light_chunks(self, n_chunks):
         """row slices of ``light`` (plans over contiguous row ranges of the same CSR arrays)"""
@@ -637,8 +652,15 @@ class BlockedRows:
             F = dZ.shape[1]
             if self._tmp is None or self._tmp.shape != (self.n_heavy, F):
                 self._tmp = ops.alloc_mat(self.n_heavy, F, dZ.device)
-            for i, blk in enumerate(self.blocks):
-                ops.spmm(blk, dZ, out=self._tmp, accumulate=(i > 0))
+            if self.stacked is not None and self._tmp.is_contiguous():
+                nb = self.stacked.shape[0] // self.n_heavy
+                if self._partial is None or self._partial.shape != (nb * self.n_heavy, F):
+                    self._partial = ops.alloc_mat(nb * self.n_heavy, F, dZ.device)
+                ops.spmm(self.stacked, dZ, out=self._partial)
+                ops.sum_slabs(self._partial, nb, self._tmp)
+            else:
+                for i, blk in enumerate(self.blocks):
+                    ops.spmm(blk, dZ, out=self._tmp, accumulate=(i > 0))
             if reduce is not None:
                 pending.append(reduce(self._tmp))
         for w in pending:

@@ -219,6 +219,9 @@ int gcg_softmax_ce_f32(const float* L, int64_t ld_l, const int32_t* y, int64_t n
 
 /* out[0] = scale * sum(x[0..n))  -- deterministic (fixed tree), single block. */
 int gcg_sum_f32(const float* x, int64_t n, float scale, float* out, void* stream);
+/* dst[i] = sum_s src[s*slab_floats + i], s ascending (deterministic): reduces the per-document-block partial rows
+ * of the blocked X^T.dZ1 product (Dot.grad of lasagne_layers.py:26,65). */
+int gcg_sum_slabs_f32(const float* src, int32_t n_slabs, int64_t slab_floats, float* dst, void* stream);
 
 /* dP[r,:] = sum over the positions p in pos_idx[pos_ptr[r] .. pos_ptr[r+1]) of G[p,:]
  * (zero where a node has no target position).  Deterministic scatter-ADD that is

@@ -303,3 +303,32 @@ def test_document_blocked_transpose_product_matches_plain():
     assert np.array_equal(got[lightrows], ref[lightrows])          # light rows: same kernel, same order
     assert_close(got[~lightrows], ref[~lightrows], atol=2e-5)      # heavy rows: block-wise summation order
     assert np.array_equal(got, br.product(to_dev(D), ops.alloc_mat(XT.shape[0], 96, "cuda")).cpu().numpy())
+
+
+def test_stacked_document_blocks_equal_the_block_loop(monkeypatch):
+    """BlockedRows: one streaming launch over all (block, heavy row) pieces + slab sum == the per-block loop."""
+    from graphconvgeo_b200 import ops
+    from graphconvgeo_b200.sparse import BlockedRows, CSRMatrix
+    rng = np.random.RandomState(21)
+    light = random_csr(rng, 300, 5000, 3)
+    heavy = sp.random(20, 5000, density=0.5, format="csr", dtype=np.float32, random_state=rng)
+    XT = sp.vstack([light[:100], heavy, light[100:]]).tocsr()
+    XT.sort_indices()
+    D = to_dev((rng.standard_normal((5000, 128)) * 0.1).astype(np.float32))
+    Xd = CSRMatrix.from_scipy(XT, long_row_threshold=512)
+    monkeypatch.setenv("GCG_XT_STACKED", "1")
+    a = BlockedRows(Xd, F=128, block_mb=0)
+    assert a.stacked is not None and a.stacked.shape[0] == a.n_heavy * len(a.blocks)
+    monkeypatch.setenv("GCG_XT_STACKED", "0")
+    b = BlockedRows(Xd, F=128, block_mb=0)
+    assert b.stacked is None
+    ra = a.product(D, ops.alloc_mat(XT.shape[0], 128, "cuda")).cpu().numpy()
+    rb = b.product(D, ops.alloc_mat(XT.shape[0], 128, "cuda")).cpu().numpy()
+    ref = np.asarray(XT @ D.cpu().numpy(), dtype=np.float32)
+    assert_close(ra, ref, atol=2e-5)
+    assert_close(ra, rb, atol=2e-5)
+    for kern in ("gather", "stream"):
+        monkeypatch.setenv("GCG_XT_STACKED", "1")
+        monkeypatch.setenv("GCG_XT_STACKED_KERNEL", kern)
+        c = BlockedRows(Xd, F=128, block_mb=0)
+        assert np.array_equal(c.product(D, ops.alloc_mat(XT.shape[0], 128, "cuda")).cpu().numpy(), ra)
