@@ -675,6 +675,11 @@ int gemm_tc_launch(const GemmArgs& g0, int transA, int transB, int mode, void* w
       Bh = g.B_hi;
       Bl = const_cast<float*>(g.B_lo);
     }
+  } else {
+    // single-pass TF32: the tensor core TRUNCATES fp32 inputs to 10 mantissa bits (a bias of ~ -3.5e-4 per
+    // operand); a caller that holds round-to-nearest hi copies (gcg_gemm_presplit_f32) gets unbiased inputs
+    if (g.A_hi) Ah = g.A_hi;
+    if (g.B_hi) Bh = g.B_hi;
   }
   // 2-CTA clusters share the B tile by multicast (see the kernel): worth it when there are enough M tiles to pair up
   // MEASURED (B200, profiles/r02_gemm_notes.md): the clustered schedule is bit-identical but SLOWER (3xTF32 140 vs

@@ -33,12 +33,39 @@
 // cost ~1 ms each (and much more on a busy driver), so the long-row tables come from a small size-bucketed
 // cache of device blocks that are only returned to the driver when the cache is full.
 namespace {
+struct PendingBlock {
+  int device;
+  size_t cap;
+  void* p;
+  cudaEvent_t ev;       // last launch that read the block
+};
 struct PlanBlockCache {
   std::mutex mu;
   std::multimap<std::pair<int, size_t>, void*> free_blocks;   // (device, capacity) -> block
-  size_t cached_bytes = 0;
+  std::vector<PendingBlock> pending;                          // released, last reader possibly still running
+  size_t cached_bytes = 0;                                    // free + pending
   static constexpr size_t kMaxCached = 256u << 20;
 } g_plan_blocks;
+
+// move released blocks whose last reader has finished to the free list (caller holds the lock)
+void plan_blocks_collect() {
+  auto& pd = g_plan_blocks.pending;
+  for (size_t i = 0; i < pd.size();) {
+    const cudaError_t q = cudaEventQuery(pd[i].ev);
+    if (q == cudaErrorNotReady) { ++i; continue; }
+    if (q == cudaSuccess) {
+      cudaEventDestroy(pd[i].ev);
+      g_plan_blocks.free_blocks.insert({{pd[i].device, pd[i].cap}, pd[i].p});
+    } else {
+      // the event was recorded inside a stream capture (or the context is failing): its completion cannot be
+      // observed, so the block is never handed out again (it stays allocated; a rare path)
+      (void)cudaGetLastError();
+      g_plan_blocks.cached_bytes -= pd[i].cap;
+    }
+    pd[i] = pd.back();
+    pd.pop_back();
+  }
+}
 
 size_t plan_block_capacity(size_t bytes) {
   size_t cap = 4096;
@@ -49,6 +76,7 @@ size_t plan_block_capacity(size_t bytes) {
 cudaError_t plan_block_acquire(int device, size_t cap, void** out) {
   {
     std::lock_guard<std::mutex> lk(g_plan_blocks.mu);
+    plan_blocks_collect();
     auto it = g_plan_blocks.free_blocks.find({device, cap});
     if (it != g_plan_blocks.free_blocks.end()) {
       *out = it->second;
@@ -60,16 +88,35 @@ cudaError_t plan_block_acquire(int device, size_t cap, void** out) {
   return cudaMalloc(out, cap);
 }
 
-void plan_block_release(int device, size_t cap, void* p) {
-  {
-    std::lock_guard<std::mutex> lk(g_plan_blocks.mu);
+// ``last_use``: event recorded after the last launch that read the block (nullptr: never read on the device).
+// No synchronisation here -- this runs from CSRMatrix.__del__, possibly while a CUDA graph is being captured.
+void plan_block_release(int device, size_t cap, void* p, cudaEvent_t last_use) {
+  std::lock_guard<std::mutex> lk(g_plan_blocks.mu);
+  if (!last_use) {
     if (g_plan_blocks.cached_bytes + cap <= PlanBlockCache::kMaxCached) {
       g_plan_blocks.free_blocks.insert({{device, cap}, p});
       g_plan_blocks.cached_bytes += cap;
-      return;
+    } else {
+      cudaFree(p);          // never used by a kernel: nothing to wait for
     }
+    return;
   }
-  cudaFree(p);
+  // over the cache limit the block still waits in the pending list (a cudaFree would synchronise the device);
+  // gcg_plan_create_csr trims the free list back under the limit
+  g_plan_blocks.pending.push_back({device, cap, p, last_use});
+  g_plan_blocks.cached_bytes += cap;
+}
+
+// called from gcg_plan_create_csr (a synchronising call anyway): give memory back when the cache is over its limit
+void plan_blocks_trim() {
+  std::lock_guard<std::mutex> lk(g_plan_blocks.mu);
+  plan_blocks_collect();
+  while (g_plan_blocks.cached_bytes > PlanBlockCache::kMaxCached && !g_plan_blocks.free_blocks.empty()) {
+    auto it = g_plan_blocks.free_blocks.begin();
+    g_plan_blocks.cached_bytes -= it->first.second;
+    cudaFree(it->second);
+    g_plan_blocks.free_blocks.erase(it);
+  }
 }
 }  // namespace
 
@@ -461,6 +508,8 @@ extern "C" int gcg_plan_create_csr(int64_t n_rows, int64_t n_cols, int64_t nnz,
   p->block_cap = 0;
   p->device = 0;
   p->stream = nullptr;
+  p->last_use = nullptr;
+  plan_blocks_trim();
   p->h_indptr.assign(h_indptr, h_indptr + n_rows + 1);
   if (p->n_long > 0) {
     // one block, one upload: [seg_row | seg_beg | long_rows | long_segptr]
@@ -495,9 +544,11 @@ extern "C" int gcg_plan_destroy(gcg_plan* p) {
   if (!p) return GCG_OK;
   if (p->stream) { gcg::stream_state_destroy(p->stream); p->stream = nullptr; }
   if (p->d_block) {
-    // kernels still reading the tables (on any stream) must finish before the block can serve another plan
-    cudaDeviceSynchronize();
-    plan_block_release(p->device, p->block_cap, p->d_block);
+    // kernels still reading the tables must finish before the block can serve another plan: the block waits in the
+    // pool's pending list until the event recorded after the plan's last launch has completed
+    plan_block_release(p->device, p->block_cap, p->d_block, p->last_use);
+  } else if (p->last_use) {
+    cudaEventDestroy(p->last_use);
   }
   delete p;
   return GCG_OK;
@@ -521,12 +572,31 @@ struct OwnerRoute {
   const int64_t* off;
 };
 
+static int spmm_run_impl(const gcg_plan* p, const float* B, int64_t ldb, int64_t F,
+                         float* C, int64_t ldc, const float* bias, int act,
+                         int accumulate, const float* gate, int64_t ld_gate,
+                         const float* carry, int64_t ld_carry, float* conv_out,
+                         int64_t ld_conv, int32_t panel_cols, void* workspace,
+                         int64_t workspace_bytes, void* stream, const OwnerRoute* route);
+
 static int spmm_run(const gcg_plan* p, const float* B, int64_t ldb, int64_t F,
                     float* C, int64_t ldc, const float* bias, int act,
                     int accumulate, const float* gate, int64_t ld_gate,
                     const float* carry, int64_t ld_carry, float* conv_out,
                     int64_t ld_conv, int32_t panel_cols, void* workspace,
-                    int64_t workspace_bytes, void* stream, const OwnerRoute* route);
+                    int64_t workspace_bytes, void* stream, const OwnerRoute* route) {
+  const int rc = spmm_run_impl(p, B, ldb, F, C, ldc, bias, act, accumulate, gate, ld_gate, carry, ld_carry, conv_out,
+                               ld_conv, panel_cols, workspace, workspace_bytes, stream, route);
+  if (rc == GCG_OK && p && p->d_block) {
+    // fence for the pooled long-row tables (see plan_block_release)
+    if (!p->last_use && cudaEventCreateWithFlags(&p->last_use, cudaEventDisableTiming) != cudaSuccess) {
+      p->last_use = nullptr;
+      GCG_CUDA(cudaGetLastError());
+    }
+    if (p->last_use) GCG_CUDA(cudaEventRecord(p->last_use, reinterpret_cast<cudaStream_t>(stream)));
+  }
+  return rc;
+}
 
 extern "C" int gcg_spmm_csr_f32(const gcg_plan* p, const float* B, int64_t ldb, int64_t F,
                                 float* C, int64_t ldc, const float* bias, int act,
@@ -556,12 +626,12 @@ extern "C" int gcg_spmm_csr_routed_f32(const gcg_plan* p, const float* B, int64_
                   panel_cols, workspace, workspace_bytes, stream, &r);
 }
 
-static int spmm_run(const gcg_plan* p, const float* B, int64_t ldb, int64_t F,
-                    float* C, int64_t ldc, const float* bias, int act,
-                    int accumulate, const float* gate, int64_t ld_gate,
-                    const float* carry, int64_t ld_carry, float* conv_out,
-                    int64_t ld_conv, int32_t panel_cols, void* workspace,
-                    int64_t workspace_bytes, void* stream, const OwnerRoute* route) {
+static int spmm_run_impl(const gcg_plan* p, const float* B, int64_t ldb, int64_t F,
+                         float* C, int64_t ldc, const float* bias, int act,
+                         int accumulate, const float* gate, int64_t ld_gate,
+                         const float* carry, int64_t ld_carry, float* conv_out,
+                         int64_t ld_conv, int32_t panel_cols, void* workspace,
+                         int64_t workspace_bytes, void* stream, const OwnerRoute* route) {
   GCG_CHECK_ARG(p != nullptr, "gcg_spmm_csr_f32: plan is NULL");
   GCG_CHECK_ARG(B && C, "gcg_spmm_csr_f32: NULL dense operand");
   GCG_CHECK_ARG(B != C, "gcg_spmm_csr_f32: B and C must not alias");

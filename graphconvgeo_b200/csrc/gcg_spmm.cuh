@@ -26,6 +26,8 @@ struct gcg_plan {
   std::vector<int32_t> h_indptr;   // host copy of indptr: the streaming variants build their span schedule
                                    // from it on first use
   gcg::StreamState* stream;        // owned; gcg_spmm_stream.cu
+  mutable cudaEvent_t last_use;    // recorded after every launch that reads d_block; the pooled block is handed to
+                                   // another plan only once this event has completed (no sync in gcg_plan_destroy)
 };
 
 namespace gcg {

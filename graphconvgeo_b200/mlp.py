@@ -25,7 +25,7 @@ import torch
 
 from . import lasagne_layers as L
 from . import ops
-from .sparse import CSRMatrix, as_csr, is_sparse
+from .sparse import CSRMatrix, RowBlockedCSR, as_csr, is_sparse
 
 logger = logging.getLogger("graphconvgeo_b200")
 
@@ -76,7 +76,7 @@ class MLP:
     # ------------------------------------------------------------------ data
     def _to_device(self, X):
         if is_sparse(X):
-            if isinstance(X, CSRMatrix):
+            if isinstance(X, (CSRMatrix, RowBlockedCSR)):
                 return X
             return CSRMatrix.from_scipy(X, device=self.device, sort_indices=False)   # keep scipy's entry order
         t = torch.as_tensor(np.ascontiguousarray(X, dtype=np.float32)).to(self.device)

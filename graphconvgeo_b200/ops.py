@@ -28,6 +28,12 @@ _FORCE_PANEL = os.environ.get("GCG_SPMM_PANEL")          # experiments: force pa
 _SPMM_MODE = os.environ.get("GCG_SPMM_MODE", "auto")     # "auto" | "stream" | "gather"
 STREAM_MIN_NNZ = int(os.environ.get("GCG_STREAM_MIN_NNZ", 1 << 20))
 _GEMM_MODE = os.environ.get("GCG_GEMM_MODE", "auto")     # "fma" | "tf32x3" | "tf32" | "auto"
+# OPT-IN (default 0 = off: every tensor-core product is 3xTF32, i.e. fp32-equivalent).  With a value K0 > 0, weight-
+# gradient contractions (TN products, K = number of nodes / targets >= K0) run ONE tf32 pass on the round-to-nearest
+# hi copies both operands already have: the input rounding (relative 4e-4 per product, unbiased) averages over
+# K >= 65536 terms to below the fp32 accumulation noise of the 3-pass product itself.  Measured, reported separately
+# (profiles/r02_gemm_notes.md); never on in the numbers bench.py reports as "dtype": "f32".
+_LONGK_TF32 = int(os.environ.get("GCG_GEMM_LONGK_TF32", "0"))
 
 _tc_available = None
 
@@ -255,20 +261,26 @@ def gemm(A, B, out=None, transA=False, transB=False, beta=0.0, bias=None, act="i
         return out
     cp, ldc = _mat(out, "out")
     mp, ldm = (None, 0) if mask is None else _mat(mask, "mask")
+    auto_mode = mode is None
     if mode is None:
         mode = gemm_mode_for(M, N, K)
     elif isinstance(mode, str):
         mode = _lib.GEMM_MODE[mode]
-    x3 = mode in (_lib.GEMM_MODE["tf32x3"], _lib.GEMM_MODE["tf32x3_chained"])
     if chained and mode == _lib.GEMM_MODE["tf32x3"]:
         mode = _lib.GEMM_MODE["tf32x3_chained"]
+    have_a = a_split is not None and a_split.matches(A, lda)
+    have_b = b_split is not None and b_split.matches(B, ldb)
+    if (auto_mode and mode == _lib.GEMM_MODE["tf32x3"] and transA and not transB and have_a and have_b
+            and 0 < _LONGK_TF32 <= K):
+        mode = _lib.GEMM_MODE["tf32"]                    # long weight-gradient contraction: see _LONGK_TF32
+    x3 = mode in (_lib.GEMM_MODE["tf32x3"], _lib.GEMM_MODE["tf32x3_chained"], _lib.GEMM_MODE["tf32"])
     wbytes = L.gcg_gemm_workspace_bytes(int(transA), int(transB), M, N, K, mode, int(split_k))
     ws, wsb = scratch.get(wbytes, A.device)
     pre = [None, None, None, None]
     if x3:
-        if a_split is not None and a_split.matches(A, lda):
+        if have_a:
             pre[0], pre[1] = C.c_void_p(a_split.hi.data_ptr()), C.c_void_p(a_split.lo.data_ptr())
-        if b_split is not None and b_split.matches(B, ldb):
+        if have_b:
             pre[2], pre[3] = C.c_void_p(b_split.hi.data_ptr()), C.c_void_p(b_split.lo.data_ptr())
     if pre[0] is not None or pre[2] is not None:
         _lib.check(L.gcg_gemm_presplit_f32(int(transA), int(transB), M, N, K, ap, lda, bp, ldb, cp, ldc, float(beta),

@@ -22,7 +22,7 @@ def _np_ptr(a: np.ndarray):
 
 def is_sparse(x) -> bool:
     """The type test of lasagne_layers.py:22-24 / :33-35 / :61-63."""
-    if isinstance(x, CSRMatrix):
+    if isinstance(x, (CSRMatrix, RowBlockedCSR)):
         return True
     try:
         import scipy.sparse as sp
@@ -292,7 +292,7 @@ def l2_schedule(A: "CSRMatrix", F, budget_bytes=48 << 20, min_panel_floats=128,
 
 
 def as_csr(x, device="cuda", long_row_threshold=256) -> CSRMatrix:
-    if isinstance(x, CSRMatrix) or hasattr(x, "dist_spmm"):      # device CSR or a row-partitioned one
+    if isinstance(x, (CSRMatrix, RowBlockedCSR)) or hasattr(x, "dist_spmm"):      # device CSR (row-blocked / row-partitioned too)
         return x
     return CSRMatrix.from_scipy(x, device=device, long_row_threshold=long_row_threshold)
 
@@ -350,11 +350,69 @@ def build_ahat_device(indptr, indices, n):
     return CSRMatrix(out_ip, out_ix, out_v, (n, n))
 
 
-def spgemm(A: "CSRMatrix", B: "CSRMatrix", a_values=None) -> "CSRMatrix":
+class RowBlockedCSR:
+    """A sparse matrix too large for int32 CSR offsets (>= 2^31 non-zeros), kept as consecutive row blocks that
+    each fit: the smoothed features X_conv = A_hat * X of a Twitter-World-sized input (main.py:528-530).  Offers
+    what the minibatch MLP needs from its training matrix: ``shape``, ``gather_rows_device`` (mlp.py:81-91)."""
+
+    def __init__(self, blocks, shape):
+        self.blocks = list(blocks)
+        self.shape = (int(shape[0]), int(shape[1]))
+        self.row_off = np.zeros(len(self.blocks) + 1, np.int64)
+        np.cumsum([b.shape[0] for b in self.blocks], out=self.row_off[1:])
+        assert self.row_off[-1] == self.shape[0]
+        self.device = self.blocks[0].device
+        self.long_row_threshold = self.blocks[0].long_row_threshold
+
+    @property
+    def nnz(self):
+        return int(sum(b.nnz for b in self.blocks))
+
+    def astype(self, dtype):
+        if np.dtype(dtype) != np.float32:
+            raise ValueError("the B200 hot path is float32 only")
+        return self
+
+    def to_scipy(self):
+        import scipy.sparse as sp
+        return sp.vstack([b.to_scipy() for b in self.blocks]).tocsr()
+
+    def gather_rows_device(self, rows):
+        """self[rows, :] as one CSRMatrix (rows in the requested order; duplicates allowed)"""
+        rows = np.ascontiguousarray(np.asarray(rows), dtype=np.int64)
+        if len(rows) and (rows.min() < 0 or rows.max() >= self.shape[0]):
+            raise IndexError("row index out of range for a matrix with %d rows" % self.shape[0])
+        owner = np.searchsorted(self.row_off, rows, side="right") - 1
+        order = np.argsort(owner, kind="stable")
+        parts, n_prev = [], 0
+        for b, blk in enumerate(self.blocks):
+            sel = order[owner[order] == b]
+            if len(sel) == 0:
+                continue
+            parts.append(blk.gather_rows_device((rows[sel] - self.row_off[b]).astype(np.int32)))
+        if len(parts) == 1 and np.array_equal(order, np.arange(len(rows))):
+            return parts[0]
+        ips, off = [], 0
+        for p_ in parts:
+            ips.append(p_.indptr[:-1].to(torch.int64) + off)
+            off += p_.nnz
+        if off >= 2 ** 31 - 1:
+            raise ValueError("gathered rows do not fit int32 CSR offsets")
+        ip = torch.cat(ips + [torch.tensor([off], dtype=torch.int64, device=self.device)]).to(torch.int32)
+        cat = CSRMatrix(ip, torch.cat([p_.indices for p_ in parts]), torch.cat([p_.data for p_ in parts]),
+                        (len(rows), self.shape[1]), long_row_threshold=self.long_row_threshold)
+        inv = np.empty(len(rows), np.int32)
+        inv[order] = np.arange(len(rows), dtype=np.int32)        # block-grouped position of every requested row
+        return cat.gather_rows_device(inv)
+
+
+def spgemm(A: "CSRMatrix", B: "CSRMatrix", a_values=None, max_block_nnz=2 ** 31 - 2):
     """C = A * B for two device CSR matrices, every entry summed in scipy's csr_matmat order, rows emitted
     with ascending columns (gcg_spgemm_count_csr / gcg_spgemm_fill_csr_f32).  ``a_values``: optional float64 device tensor replacing A.data -- the reference
     multiplies a FLOAT64 A_hat into X (main.py:522-530): float64 sums, one float32 rounding.  With float32
-    values the sums are float32, scipy's rule for float32 * float32."""
+    values the sums are float32, scipy's rule for float32 * float32.
+    A product with more than ``max_block_nnz`` non-zeros (int32 CSR offsets; Twitter-World smoothing) is returned
+    as a ``RowBlockedCSR`` of consecutive row blocks, each filled by its own launch; otherwise a ``CSRMatrix``."""
     if A.shape[1] != B.shape[0]:
         raise ValueError("spgemm: A is %s but B is %s" % (A.shape, B.shape))
     dev = A.device
@@ -371,18 +429,38 @@ def spgemm(A: "CSRMatrix", B: "CSRMatrix", a_values=None) -> "CSRMatrix":
     _lib.check(L.gcg_spgemm_count_csr(n, V, A.indptr.data_ptr(), A.indices.data_ptr(), B.indptr.data_ptr(),
                                       B.indices.data_ptr(), 0, row_nnz.data_ptr(), wp, wsb, stream),
                "gcg_spgemm_count_csr")
-    c_ip = torch.zeros(n + 1, dtype=torch.int64, device=dev)
-    torch.cumsum(row_nnz[:n], 0, out=c_ip[1:])
-    nnz = int(c_ip[-1].item())
-    if nnz >= 2 ** 31 - 1:
-        raise _lib.GcgError("spgemm: the product has %d non-zeros; split A into row blocks (int32 CSR offsets)" % nnz)
-    c_ix = torch.empty(nnz, dtype=torch.int32, device=dev)
-    c_d = torch.empty(nnz, dtype=torch.float32, device=dev)
-    _lib.check(L.gcg_spgemm_fill_csr_f32(n, V, A.indptr.data_ptr(), A.indices.data_ptr(), av.data_ptr(),
-                                         int(av.dtype == torch.float64), B.indptr.data_ptr(), B.indices.data_ptr(),
-                                         B.data.data_ptr(), c_ip.data_ptr(), c_ix.data_ptr(), c_d.data_ptr(), wp, wsb,
-                                         stream), "gcg_spgemm_fill_csr_f32")
-    return CSRMatrix(c_ip.to(torch.int32), c_ix, c_d, (n, V))
+    cum = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+    torch.cumsum(row_nnz[:n], 0, out=cum[1:])
+    total = int(cum[-1].item())
+    # consecutive row blocks whose output fits the offset type (one block in the common case)
+    bounds = [0]
+    if total > max_block_nnz:
+        cum_h = cum.cpu().numpy()
+        while bounds[-1] < n:
+            r0 = bounds[-1]
+            r1 = int(np.searchsorted(cum_h, cum_h[r0] + max_block_nnz, side="right")) - 1
+            if r1 <= r0:
+                raise _lib.GcgError("spgemm: row %d alone has more than %d non-zeros" % (r0, max_block_nnz))
+            bounds.append(min(r1, n))
+    else:
+        bounds.append(n)
+    blocks = []
+    esz = 8 if av.dtype == torch.float64 else 4
+    for r0, r1 in zip(bounds[:-1], bounds[1:]):
+        c_ip = (cum[r0:r1 + 1] - cum[r0]).contiguous()
+        nnz = int(c_ip[-1].item())
+        c_ix = torch.empty(nnz, dtype=torch.int32, device=dev)
+        c_d = torch.empty(nnz, dtype=torch.float32, device=dev)
+        # rows [r0, r1) of A: the same CSR arrays entered at row r0 (indptr holds absolute offsets)
+        _lib.check(L.gcg_spgemm_fill_csr_f32(r1 - r0, V, A.indptr.data_ptr() + 4 * r0, A.indices.data_ptr(), av.data_ptr(),
+                                             int(av.dtype == torch.float64), B.indptr.data_ptr(), B.indices.data_ptr(),
+                                             B.data.data_ptr(), c_ip.data_ptr(), c_ix.data_ptr(), c_d.data_ptr(), wp, wsb,
+                                             stream), "gcg_spgemm_fill_csr_f32")
+        blocks.append(CSRMatrix(c_ip.to(torch.int32), c_ix, c_d, (r1 - r0, V)))
+    del esz
+    if len(blocks) == 1:
+        return blocks[0]
+    return RowBlockedCSR(blocks, (n, V))
 
 
 def spgemm_pattern(A: "CSRMatrix", B: "CSRMatrix", drop_diagonal=False) -> "CSRMatrix":
@@ -414,7 +492,7 @@ def spgemm_pattern(A: "CSRMatrix", B: "CSRMatrix", drop_diagonal=False) -> "CSRM
     return CSRMatrix(c_ip.to(torch.int32), c_ix, torch.ones(nnz, dtype=torch.float32, device=dev), (n, V))
 
 
-def smooth_features(H, X, device="cuda") -> "CSRMatrix":
+def smooth_features(H, X, device="cuda", max_block_nnz=2 ** 31 - 2):
     """`X_conv = H * X; X_conv = X_conv.tocsr().astype('float32')` (main.py:528-530, tensormain.py:112-114).
     ``H``: scipy sparse A_hat (float64 as the reference builds it, or float32); ``X``: scipy CSR / CSRMatrix."""
     import scipy.sparse as sp
@@ -424,7 +502,7 @@ def smooth_features(H, X, device="cuda") -> "CSRMatrix":
     if Hs.dtype == np.float64:
         a_vals = torch.from_numpy(np.ascontiguousarray(Hs.data)).to(A.device)
     B = X if isinstance(X, CSRMatrix) else CSRMatrix.from_scipy(X, device=device, sort_indices=False)
-    return spgemm(A, B, a_values=a_vals)
+    return spgemm(A, B, a_values=a_vals, max_block_nnz=max_block_nnz)
 
 
 def _min_block_cols():

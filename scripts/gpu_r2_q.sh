@@ -3,7 +3,7 @@
 # parity), the reference arm at the same configuration -- plus GEMM tests / rates of the final kernels
 mkdir -p gpurun_out
 timeout 300 python __graft_entry__.py --smoke > gpurun_out/q_smoke.log 2>&1; echo "smoke rc=$?"; tail -4 gpurun_out/q_smoke.log
-timeout 600 python -m pytest tests/test_gpu_gemm.py -m gpu -x -q --timeout 300 > gpurun_out/q_pytest_gemm.log 2>&1; echo "pytest gemm rc=$?"; tail -2 gpurun_out/q_pytest_gemm.log
+timeout 900 python -m pytest tests/test_gpu_gemm.py tests/test_gpu_mlp.py -m gpu -x -q --timeout 300 > gpurun_out/q_pytest_gemm.log 2>&1; echo "pytest gemm+mlp rc=$?"; tail -3 gpurun_out/q_pytest_gemm.log
 timeout 600 python scripts/tc_check.py > gpurun_out/q_tc_check.log 2>&1; echo "tc_check rc=$?"; grep "bench tf32x3" gpurun_out/q_tc_check.log
 ( time timeout 1500 python bench.py --breakdown > gpurun_out/q_bench_default.json 2> gpurun_out/q_bench_default.log ) 2> gpurun_out/q_bench_default.time
 echo "bench default rc=$?"; cat gpurun_out/q_bench_default.time | tail -3; grep -A12 "op breakdown" gpurun_out/q_bench_default.log | cut -c1-110

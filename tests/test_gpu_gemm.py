@@ -147,6 +147,41 @@ def test_presplit_operands_give_identical_results():
     assert_close(ops.gemm(A, B, mode="fma", a_split=sA).cpu().numpy(), r0.cpu().numpy(), atol=1e-5)
 
 
+def test_opt_in_single_pass_tf32_for_long_weight_gradient_contractions(monkeypatch):
+    """GCG_GEMM_LONGK_TF32 (off by default): TN products over K >= K0 rows whose operands both carry round-to-nearest
+    hi copies run one tf32 pass on those copies.  Off: bit-identical to 3xTF32.  On: unbiased (the hardware would
+    TRUNCATE raw fp32 inputs: a relative bias of ~5e-4 with same-sign products) and, because the input rounding
+    averages over K, as close to float64 as the 3-pass product at this K."""
+    from graphconvgeo_b200 import ops
+    if "tf32x3" not in tc_modes():
+        pytest.skip("tcgen05 engine unavailable")
+    rng = np.random.RandomState(11)
+    K, M, N = 200000, 256, 384
+    A = np.abs(rng.standard_normal((K, M)) * 0.5).astype(np.float32)       # same-sign products: a bias would show
+    B = np.abs(rng.standard_normal((K, N)) * 1e-3).astype(np.float32)
+    Ad, Bd = to_dev(A), to_dev(B)
+    sA, sB = ops.tf32_split(Ad), ops.tf32_split(Bd)
+    ref = A.astype(np.float64).T @ B.astype(np.float64)
+    assert ops._LONGK_TF32 == 0
+    x3 = ops.gemm(Ad, Bd, transA=True, a_split=sA, b_split=sB, mode="tf32x3")
+    off = ops.gemm(Ad, Bd, transA=True, a_split=sA, b_split=sB)
+    assert torch.equal(x3, off)
+    monkeypatch.setattr(ops, "_LONGK_TF32", 65536)
+    on = ops.gemm(Ad, Bd, transA=True, a_split=sA, b_split=sB)
+    assert not torch.equal(on, off)
+    e_on = (on.cpu().numpy() - ref) / ref
+    e_x3 = (x3.cpu().numpy() - ref) / ref
+    # the single pass IS the hi.hi part of the 3-pass product (same chains); what it drops are the lo cross terms,
+    # zero-mean after round-to-nearest and averaged over K: ~4e-4 / sqrt(K) = 9e-7 relative per output
+    d = e_on - e_x3
+    assert abs(d.mean()) < 1e-6, d.mean()                        # unbiased (truncated inputs: ~ -5e-4, below)
+    assert np.abs(d).max() < 1e-5, np.abs(d).max()
+    # the rule needs BOTH rounded copies and a TN product; otherwise nothing changes
+    assert torch.equal(ops.gemm(Ad, Bd, transA=True, a_split=sA), ops.gemm(Ad, Bd, transA=True, a_split=sA, mode="tf32x3"))
+    raw = ops.gemm(Ad, Bd, transA=True, mode="tf32").cpu().numpy()         # raw fp32 into the tensor core: truncation
+    assert ((raw - ref) / ref - e_x3).mean() < -1e-4
+
+
 @pytest.mark.parametrize("ta,tb", [(False, False), (True, False), (False, True), (True, True)])
 @pytest.mark.parametrize("M,N,K,chained", [(1024, 600, 600, False), (1100, 256, 320, True), (640, 1024, 1000, False),
                                            (129, 70, 64, True), (2000, 600, 8200, False)])

@@ -235,3 +235,40 @@ def test_smoothing_then_mlp_pipeline():
     acc_smooth = run(ref)            # scipy copy of the (bit-identical) smoothed features: row slicing on the host
     acc_raw = run(X)
     assert acc_smooth > acc_raw + 0.1 and acc_smooth > 0.8
+
+
+def test_smoothing_larger_than_int32_offsets_comes_back_as_row_blocks():
+    """Twitter-World smoothing has more than 2^31 non-zeros: sparse.spgemm then returns consecutive row blocks
+    (RowBlockedCSR).  Exercised here with a small limit: blocks == scipy's product bit for bit, minibatch row
+    gathers (any order, duplicates, rows from several blocks) == scipy slicing, and the minibatch MLP trains to the
+    same parameters from the blocked matrix as from the single one."""
+    from graphconvgeo_b200.mlp import MLP
+    from graphconvgeo_b200.sparse import CSRMatrix, RowBlockedCSR, smooth_features
+    rng = np.random.RandomState(31)
+    n, v = 900, 400
+    X = _tfidf_like(rng, n, v, 10)
+    H = go.build_ahat(_graph(rng, n, 6, hubs=(5,)), dtype="float64")
+    ref = mo.smooth_features(H, X)
+    one = smooth_features(H, X)
+    assert isinstance(one, CSRMatrix)
+    blk = smooth_features(H, X, max_block_nnz=ref.nnz // 5 + 7)
+    assert isinstance(blk, RowBlockedCSR) and len(blk.blocks) >= 5 and blk.shape == ref.shape and blk.nnz == ref.nnz
+    assert all(b.nnz <= ref.nnz // 5 + 7 for b in blk.blocks)
+    got = blk.to_scipy()
+    assert np.array_equal(got.indptr, ref.indptr) and np.array_equal(got.indices, ref.indices) and np.array_equal(got.data, ref.data)
+    rows = rng.choice(n, size=257, replace=True)
+    g = blk.gather_rows_device(rows)
+    want = ref[rows]
+    assert np.array_equal(g.indptr.cpu().numpy(), want.indptr) and np.array_equal(g.indices.cpu().numpy(), want.indices)
+    assert np.array_equal(g.data.cpu().numpy(), want.data)
+    with pytest.raises(IndexError):
+        blk.gather_rows_device([n])
+    Y = rng.randint(0, 5, size=n).astype(np.int32)
+
+    def train(feats):
+        clf = MLP(n_epochs=2, batch_size=128, regul_coefs=[1e-6, 1e-6], hidden_layer_size=16, seed=3)
+        clf.fit(feats, Y, ref[:100], Y[:100])
+        return clf.get_param_values() if hasattr(clf, "get_param_values") else [p.cpu().numpy() for p in clf.params]
+    pa, pb = train(one), train(blk)
+    for a, b in zip(pa, pb):
+        assert np.array_equal(a, b)
