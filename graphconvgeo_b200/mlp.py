@@ -194,7 +194,7 @@ class MLP:
 
     # -------------------------------------------------------------------- fit
     def _batch(self, X, idx):
-        if isinstance(X, CSRMatrix):
+        if isinstance(X, (CSRMatrix, RowBlockedCSR)):
             return X.gather_rows_device(idx)
         return ops.gather_rows(X, torch.from_numpy(np.ascontiguousarray(idx, dtype=np.int32)).to(self.device))
 
