@@ -450,7 +450,11 @@ def run_gpu(args):
                            "peer-memory stores over NVLink" if getattr(getattr(m, "part", None), "peer", None) is not None
                            else "NCCL all-to-all")) if getattr(m, "partition", "") == "feature" else "row blocks + NCCL all-gather"))
                        if world > 1 else "single GPU",
-                       gemm_mode=os.environ.get("GCG_GEMM_MODE", "auto")),
+                       gemm_mode=os.environ.get("GCG_GEMM_MODE", "auto"),
+                       epoch_driver=("gcg_epoch_run (the epoch recorded as a C++ call list, include/gcg.h), captured in a CUDA graph"
+                                     if getattr(m, "_program", None) is not None else
+                                     ("layer code captured in a CUDA graph" if getattr(m, "_graph", None) is not None
+                                      else "layer code, eager"))),
         "clocks": sampler.summary(), "gpu_launches": launches * args.steps,
         "launches_per_epoch": launches, "loss": loss, "acc": acc,
     }

@@ -66,6 +66,13 @@ PROTOTYPES = {
     "gcg_adam_workspace_bytes": (c_i64, [c_i32, C.POINTER(c_i64)]),
     "gcg_elastic_net_f32": (c_int, [c_i32, C.POINTER(c_vp), C.POINTER(c_i64), C.POINTER(c_f32), c_vp, c_vp,
                                     c_i64, c_vp]),
+    "gcg_epoch_create": (c_int, [C.POINTER(c_vp)]),
+    "gcg_epoch_destroy": (c_int, [c_vp]),
+    "gcg_epoch_record_begin": (c_int, [c_vp]),
+    "gcg_epoch_record_end": (c_int, [c_vp]),
+    "gcg_epoch_size": (c_i64, [c_vp]),
+    "gcg_epoch_call_name": (C.c_char_p, [c_vp, c_i64]),
+    "gcg_epoch_run": (c_int, [c_vp, c_vp]),
     "gcg_kdtree_fit_host": (c_int, [c_vp, c_i64, c_i32, c_i64, c_vp, C.POINTER(c_i64)]),
     "gcg_ahat_nnz_host": (c_i64, [c_i64, c_vp, c_vp]),
     "gcg_ahat_build_host": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),

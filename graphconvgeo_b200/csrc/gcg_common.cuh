@@ -5,6 +5,8 @@
 #include <stdio.h>
 #include <stdarg.h>
 
+#include <functional>
+
 #include "gcg.h"
 
 namespace gcg {
@@ -51,6 +53,17 @@ void count_launch(int n = 1);
   } while (0)
 
 constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
+
+// ---- epoch programs (gcg_epoch_*, gcg_core.cu) --------------------------------
+// While a thread records, every stream-taking compute entry point appends a closure of itself (its arguments by
+// value, host-side tables deep-copied, the stream left open) to the program, and still runs.  gcg_epoch_run()
+// calls the closures in order on the stream it is given: the host-side C++ epoch of SURVEY section 8 row a13.
+bool epoch_recording();
+void epoch_record(const char* name, std::function<int(void*)> call);
+#define GCG_RECORD(NAME, CALL)                                                              \
+  do {                                                                                      \
+    if (gcg::epoch_recording()) gcg::epoch_record(NAME, [=](void* s__) -> int { return CALL; }); \
+  } while (0)
 
 __host__ __device__ static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }

@@ -3,6 +3,8 @@
 // it, grids sized in multiples of the SM count, deterministic reductions.
 #include <algorithm>
 
+#include <vector>
+
 #include "gcg_common.cuh"
 
 namespace gcg {
@@ -413,6 +415,7 @@ __global__ void __launch_bounds__(256) sum_slabs_kernel(const float4* __restrict
 }
 
 extern "C" int gcg_sum_slabs_f32(const float* src, int32_t n_slabs, int64_t slab_floats, float* dst, void* stream) {
+  GCG_RECORD("gcg_sum_slabs_f32", gcg_sum_slabs_f32(src, n_slabs, slab_floats, dst, s__));
   GCG_CHECK_ARG(src && dst && n_slabs > 0 && slab_floats >= 0, "gcg_sum_slabs_f32: bad argument");
   GCG_CHECK_SHAPE(slab_floats % 4 == 0 && aligned16(src) && aligned16(dst), "gcg_sum_slabs_f32: needs 16-byte aligned slabs of 4k floats");
   if (slab_floats == 0) return GCG_OK;
@@ -431,6 +434,7 @@ extern "C" int64_t gcg_colsum_workspace_bytes(int64_t n_rows, int64_t F) {
 
 extern "C" int gcg_colsum_f32(const float* X, int64_t ld, int64_t n_rows, int64_t F, float* out,
                               void* workspace, int64_t workspace_bytes, void* stream) {
+  GCG_RECORD("gcg_colsum_f32", gcg_colsum_f32(X, ld, n_rows, F, out, workspace, workspace_bytes, s__));
   GCG_CHECK_ARG(X && out, "gcg_colsum_f32: NULL argument");
   GCG_CHECK_SHAPE(F > 0 && n_rows >= 0 && ld >= F, "gcg_colsum_f32: bad shape n=%lld F=%lld ld=%lld",
                   (long long)n_rows, (long long)F, (long long)ld);
@@ -459,6 +463,7 @@ extern "C" int gcg_colsum_f32(const float* X, int64_t ld, int64_t n_rows, int64_
 extern "C" int gcg_act_bwd_f32(const float* dA, int64_t ld_da, const float* A, int64_t ld_a,
                                float* dP, int64_t ld_dp, int64_t n_rows, int64_t F, int act,
                                void* stream) {
+  GCG_RECORD("gcg_act_bwd_f32", gcg_act_bwd_f32(dA, ld_da, A, ld_a, dP, ld_dp, n_rows, F, act, s__));
   GCG_CHECK_ARG(dA && A && dP, "gcg_act_bwd_f32: NULL argument");
   GCG_CHECK_SHAPE(F > 0 && ld_da >= F && ld_a >= F && ld_dp >= F, "gcg_act_bwd_f32: bad leading dimension");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -478,6 +483,7 @@ extern "C" int gcg_highway_bwd_f32(const float* dO, int64_t ld_do, const float* 
                                    float* dP, int64_t ld_dp, float* dGpre, int64_t ld_dg,
                                    float* dHin, int64_t ld_dh, int64_t n_rows, int64_t F, int act,
                                    void* stream) {
+  GCG_RECORD("gcg_highway_bwd_f32", gcg_highway_bwd_f32(dO, ld_do, g, ld_g, Hc, ld_hc, Hin, ld_hin, dP, ld_dp, dGpre, ld_dg, dHin, ld_dh, n_rows, F, act, s__));
   GCG_CHECK_ARG(dO && g && Hc && Hin && dP && dGpre && dHin, "gcg_highway_bwd_f32: NULL argument");
   GCG_CHECK_SHAPE(F > 0 && ld_do >= F && ld_g >= F && ld_hc >= F && ld_hin >= F && ld_dp >= F &&
                       ld_dg >= F && ld_dh >= F,
@@ -500,6 +506,7 @@ extern "C" int gcg_highway_bwd_f32(const float* dO, int64_t ld_do, const float* 
 extern "C" int gcg_softmax_ce_f32(const float* L, int64_t ld_l, const int32_t* y, int64_t n_idx,
                                   int64_t C, float denom, float* probs, int64_t ld_p, float* G,
                                   int64_t ld_g, float* ce, float* hit, int64_t* pred, void* stream) {
+  GCG_RECORD("gcg_softmax_ce_f32", gcg_softmax_ce_f32(L, ld_l, y, n_idx, C, denom, probs, ld_p, G, ld_g, ce, hit, pred, s__));
   GCG_CHECK_ARG(L != nullptr, "gcg_softmax_ce_f32: logits NULL");
   GCG_CHECK_SHAPE(C > 0 && ld_l >= C && (!probs || ld_p >= C) && (!G || ld_g >= C),
                   "gcg_softmax_ce_f32: bad shape C=%lld", (long long)C);
@@ -514,6 +521,7 @@ extern "C" int gcg_softmax_ce_f32(const float* L, int64_t ld_l, const int32_t* y
 }
 
 extern "C" int gcg_sum_f32(const float* x, int64_t n, float scale, float* out, void* stream) {
+  GCG_RECORD("gcg_sum_f32", gcg_sum_f32(x, n, scale, out, s__));
   GCG_CHECK_ARG(out && (x || n == 0), "gcg_sum_f32: NULL argument");
   sum_kernel<<<1, 1024, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, n, scale, out);
   GCG_LAUNCH_CHECK();
@@ -523,6 +531,7 @@ extern "C" int gcg_sum_f32(const float* x, int64_t n, float scale, float* out, v
 extern "C" int gcg_scatter_rows_f32(const float* G, int64_t ld_g, const int32_t* pos_ptr,
                                     const int32_t* pos_idx, int64_t n_rows, int64_t C, float* dP,
                                     int64_t ld_dp, void* stream) {
+  GCG_RECORD("gcg_scatter_rows_f32", gcg_scatter_rows_f32(G, ld_g, pos_ptr, pos_idx, n_rows, C, dP, ld_dp, s__));
   GCG_CHECK_ARG(G && pos_ptr && pos_idx && dP, "gcg_scatter_rows_f32: NULL argument");
   GCG_CHECK_SHAPE(C > 0 && ld_g >= C && ld_dp >= C, "gcg_scatter_rows_f32: bad leading dimension");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -537,6 +546,7 @@ extern "C" int gcg_scatter_rows_f32(const float* G, int64_t ld_g, const int32_t*
 
 extern "C" int gcg_gather_rows_f32(const float* X, int64_t ld_x, const int32_t* idx, int64_t n_idx,
                                    int64_t C, float* out, int64_t ld_out, void* stream) {
+  GCG_RECORD("gcg_gather_rows_f32", gcg_gather_rows_f32(X, ld_x, idx, n_idx, C, out, ld_out, s__));
   GCG_CHECK_ARG(X && idx && out, "gcg_gather_rows_f32: NULL argument");
   GCG_CHECK_SHAPE(C > 0 && ld_x >= C && ld_out >= C, "gcg_gather_rows_f32: bad leading dimension");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -565,6 +575,17 @@ extern "C" int gcg_adam_step_f32(int32_t n_tensors, float* const* h_params, cons
                                  const float* h_reg, float lr, float beta1, float beta2, float eps,
                                  float* d_t, float* reg_out, void* workspace, int64_t workspace_bytes,
                                  void* stream) {
+  if (gcg::epoch_recording() && n_tensors > 0 && h_params && h_grads && h_m && h_v && h_sizes && h_reg) {
+    // the pointer / size / coefficient tables live on the host: the closure keeps its own copies
+    std::vector<float*> cp(h_params, h_params + n_tensors), cm(h_m, h_m + n_tensors), cv(h_v, h_v + n_tensors);
+    std::vector<const float*> cg(h_grads, h_grads + n_tensors);
+    std::vector<int64_t> cs(h_sizes, h_sizes + n_tensors);
+    std::vector<float> cr(h_reg, h_reg + n_tensors);
+    gcg::epoch_record("gcg_adam_step_f32", [=](void* s__) -> int {
+      return gcg_adam_step_f32(n_tensors, cp.data(), cg.data(), cm.data(), cv.data(), cs.data(), cr.data(), lr, beta1,
+                               beta2, eps, d_t, reg_out, workspace, workspace_bytes, s__);
+    });
+  }
   GCG_CHECK_ARG(n_tensors > 0 && n_tensors <= kAdamMaxTensors, "gcg_adam_step_f32: n_tensors=%d (max %d)",
                 n_tensors, kAdamMaxTensors);
   GCG_CHECK_ARG(h_params && h_grads && h_m && h_v && h_sizes && d_t, "gcg_adam_step_f32: NULL argument");
@@ -604,6 +625,14 @@ extern "C" int gcg_adam_step_f32(int32_t n_tensors, float* const* h_params, cons
 extern "C" int gcg_elastic_net_f32(int32_t n_tensors, const float* const* h_params, const int64_t* h_sizes,
                                    const float* h_reg, float* out, void* workspace,
                                    int64_t workspace_bytes, void* stream) {
+  if (gcg::epoch_recording() && n_tensors > 0 && h_params && h_sizes && h_reg) {
+    std::vector<const float*> cp(h_params, h_params + n_tensors);
+    std::vector<int64_t> cs(h_sizes, h_sizes + n_tensors);
+    std::vector<float> cr(h_reg, h_reg + n_tensors);
+    gcg::epoch_record("gcg_elastic_net_f32", [=](void* s__) -> int {
+      return gcg_elastic_net_f32(n_tensors, cp.data(), cs.data(), cr.data(), out, workspace, workspace_bytes, s__);
+    });
+  }
   GCG_CHECK_ARG(n_tensors > 0 && n_tensors <= kAdamMaxTensors, "gcg_elastic_net_f32: n_tensors=%d (max %d)",
                 n_tensors, kAdamMaxTensors);
   GCG_CHECK_ARG(h_params && h_sizes && h_reg && out, "gcg_elastic_net_f32: NULL argument");
@@ -634,6 +663,7 @@ extern "C" int gcg_elastic_net_f32(int32_t n_tensors, const float* const* h_para
 extern "C" int gcg_highway_fwd_f32(const float* Hc, int64_t ld_hc, const float* g, int64_t ld_g,
                                    const float* Hin, int64_t ld_hin, float* O, int64_t ld_o,
                                    int64_t n_rows, int64_t F, void* stream) {
+  GCG_RECORD("gcg_highway_fwd_f32", gcg_highway_fwd_f32(Hc, ld_hc, g, ld_g, Hin, ld_hin, O, ld_o, n_rows, F, s__));
   GCG_CHECK_ARG(Hc && g && Hin && O, "gcg_highway_fwd_f32: NULL argument");
   GCG_CHECK_SHAPE(F > 0 && ld_hc >= F && ld_g >= F && ld_hin >= F && ld_o >= F, "gcg_highway_fwd_f32: bad leading dimension");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -648,6 +678,7 @@ extern "C" int gcg_highway_fwd_f32(const float* Hc, int64_t ld_hc, const float* 
 
 extern "C" int gcg_pack_cols_f32(const float* src, int64_t ld, int64_t n_rows, int64_t F, int32_t P, int64_t Fp,
                                  float* dst, void* stream) {
+  GCG_RECORD("gcg_pack_cols_f32", gcg_pack_cols_f32(src, ld, n_rows, F, P, Fp, dst, s__));
   GCG_CHECK_ARG(src && dst && P > 0, "gcg_pack_cols_f32: bad argument");
   GCG_CHECK_SHAPE(Fp % 4 == 0 && ld % 4 == 0 && ld >= F && (int64_t)P * Fp >= F && aligned16(src) && aligned16(dst),
                   "gcg_pack_cols_f32: needs 16-byte aligned operands, ld %% 4 == 0, Fp %% 4 == 0");
@@ -660,6 +691,7 @@ extern "C" int gcg_pack_cols_f32(const float* src, int64_t ld, int64_t n_rows, i
 
 extern "C" int gcg_unpack_cols_f32(const float* src, int64_t n_rows, int64_t F, int32_t P, int64_t Fp, float* dst,
                                    int64_t ld, void* stream) {
+  GCG_RECORD("gcg_unpack_cols_f32", gcg_unpack_cols_f32(src, n_rows, F, P, Fp, dst, ld, s__));
   GCG_CHECK_ARG(src && dst && P > 0, "gcg_unpack_cols_f32: bad argument");
   GCG_CHECK_SHAPE(Fp % 4 == 0 && ld % 4 == 0 && ld >= F && (int64_t)P * Fp >= F && aligned16(src) && aligned16(dst),
                   "gcg_unpack_cols_f32: needs 16-byte aligned operands, ld %% 4 == 0, Fp %% 4 == 0");

@@ -202,6 +202,7 @@ extern "C" int gcg_gemm_f32(int transA, int transB, int64_t M, int64_t N, int64_
                             int64_t ldc, float beta, const float* bias, int act, const float* mask,
                             int64_t ld_mask, int mask_act, int mode, int32_t split_k,
                             void* workspace, int64_t workspace_bytes, void* stream) {
+  GCG_RECORD("gcg_gemm_f32", gcg_gemm_f32(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, beta, bias, act, mask, ld_mask, mask_act, mode, split_k, workspace, workspace_bytes, s__));
   return gemm_impl(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, beta, bias, act, mask, ld_mask, mask_act, mode,
                    split_k, workspace, workspace_bytes, stream, nullptr, nullptr, nullptr, nullptr);
 }
@@ -212,6 +213,7 @@ extern "C" int gcg_gemm_presplit_f32(int transA, int transB, int64_t M, int64_t 
                                      int64_t ld_mask, int mask_act, int mode, int32_t split_k,
                                      void* workspace, int64_t workspace_bytes, void* stream,
                                      const float* A_hi, const float* A_lo, const float* B_hi, const float* B_lo) {
+  GCG_RECORD("gcg_gemm_presplit_f32", gcg_gemm_presplit_f32(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, beta, bias, act, mask, ld_mask, mask_act, mode, split_k, workspace, workspace_bytes, s__, A_hi, A_lo, B_hi, B_lo));
   GCG_CHECK_ARG((A_hi == nullptr) == (A_lo == nullptr) && (B_hi == nullptr) == (B_lo == nullptr),
                 "gcg_gemm_presplit_f32: hi and lo go together");
   return gemm_impl(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, beta, bias, act, mask, ld_mask, mask_act, mode,

@@ -763,6 +763,7 @@ int gemm_tc_launch(const GemmArgs& g0, int transA, int transB, int mode, void* w
 }  // namespace gcg
 
 extern "C" int gcg_tf32_split_f32(const float* x, int64_t ld, int64_t n_rows, float* hi, float* lo, void* stream) {
+  GCG_RECORD("gcg_tf32_split_f32", gcg_tf32_split_f32(x, ld, n_rows, hi, lo, s__));
   GCG_CHECK_ARG(x && hi && lo && n_rows >= 0, "gcg_tf32_split_f32: NULL argument");
   GCG_CHECK_SHAPE(ld % 4 == 0 && gcg::aligned16(x) && gcg::aligned16(hi) && gcg::aligned16(lo),
                   "gcg_tf32_split_f32: needs 16-byte aligned operands and ld %% 4 == 0");

@@ -604,6 +604,7 @@ extern "C" int gcg_spmm_csr_f32(const gcg_plan* p, const float* B, int64_t ldb, 
                                 const float* carry, int64_t ld_carry, float* conv_out,
                                 int64_t ld_conv, int32_t panel_cols, void* workspace,
                                 int64_t workspace_bytes, void* stream) {
+  GCG_RECORD("gcg_spmm_csr_f32", gcg_spmm_csr_f32(p, B, ldb, F, C, ldc, bias, act, accumulate, gate, ld_gate, carry, ld_carry, conv_out, ld_conv, panel_cols, workspace, workspace_bytes, s__));
   return spmm_run(p, B, ldb, F, C, ldc, bias, act, accumulate, gate, ld_gate, carry, ld_carry, conv_out, ld_conv,
                   panel_cols, workspace, workspace_bytes, stream, nullptr);
 }

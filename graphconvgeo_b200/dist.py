@@ -469,6 +469,7 @@ class DistMLPCONV(MLPCONV):
 
     def __init__(self, *args, group=None, partition="auto", peer_memory=True, **kwargs):
         kwargs["cuda_graph"] = False          # NCCL work is enqueued eagerly
+        kwargs["native_epoch"] = False        # collectives and peer barriers are not part of a gcg_epoch
         super().__init__(*args, **kwargs)
         assert partition in ("row", "feature", "auto")
         if partition == "auto":               # measured on B200: the all-gather wins at 2 ranks, the transposes from 4 up

@@ -52,7 +52,8 @@ class MLPCONV:
                  cuda_graph=True,
                  model_dir=None,
                  learning_rate=4e-3,
-                 reorder="auto"):
+                 reorder="auto",
+                 native_epoch=None):
         # mlpconv.py:136-150
         self.n_epochs = n_epochs
         self.batch_size = batch_size          # accepted and ignored: full batch (mlpconv.py:294)
@@ -74,6 +75,8 @@ class MLPCONV:
         self.device = torch.device(device)
         self.seed = seed
         self.cuda_graph = cuda_graph
+        # the epoch as a native gcg_epoch object (see f_train); None = the GCG_NATIVE_EPOCH environment switch
+        self.native_epoch = (os.environ.get("GCG_NATIVE_EPOCH", "0") != "0") if native_epoch is None else bool(native_epoch)
         self.model_dir = model_dir
         self.learning_rate = learning_rate
         self.reorder = reorder      # None | "auto" | "labels" | "degree" | explicit permutation (new -> old)
@@ -182,12 +185,27 @@ class MLPCONV:
         self._train_hb = hb
 
     def f_train(self):
+        """One epoch (mlpconv.py:295).  The first call runs the layer code eagerly (buffers get allocated); after
+        that the epoch is a compiled object, as the reference's Theano function is: with ``native_epoch`` the
+        second call records the step into a gcg_epoch (C++ list of every libgcg call, include/gcg.h) which later
+        calls replay with one C call -- optionally itself captured in a CUDA graph; without it the layer code is
+        captured in a CUDA graph directly."""
         if self._graph is not None:
             self._graph.replay()
+        elif self._program is not None:
+            self._program.run()
+        elif self.native_epoch and self._steps_done >= 1 and not self.drop_out:
+            prog = ops.EpochProgram()
+            with prog.record():
+                self._train_step_enqueue()
+            self._program = prog
+            self._steps_done += 1
+            if self.cuda_graph:
+                self._capture()
         else:
             self._train_step_enqueue()
             self._steps_done += 1
-            if self.cuda_graph and self._steps_done == 1 and not self.drop_out:
+            if self.cuda_graph and not self.native_epoch and self._steps_done == 1 and not self.drop_out:
                 self._capture()
         return self._train_hb
 
@@ -195,7 +213,10 @@ class MLPCONV:
         torch.cuda.synchronize(self.device)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            self._train_step_enqueue()
+            if self._program is not None:
+                self._program.run()
+            else:
+                self._train_step_enqueue()
         self._graph = g
 
     def train_results(self):
@@ -286,6 +307,7 @@ class MLPCONV:
         self.y_dev_dev = to_dev(Y_dev)
         self._heads = {}
         self._graph = None
+        self._program = None
         self._steps_done = 0
         self._train_hb = None
         return self

@@ -107,8 +107,11 @@ class _Scratch:
     """One growing scratch buffer per (device, stream): all libgcg calls on a
     stream are ordered, so consecutive ops can share it."""
 
-    def __init__(self):
+    def __init__(self, keep_outgrown=False):
         self.bufs = {}
+        # an epoch program holds the pointers it was recorded with: buffers a later call outgrew stay allocated
+        self.keep_outgrown = keep_outgrown
+        self.outgrown = []
 
     def get(self, nbytes, device):
         if nbytes <= 0:
@@ -116,6 +119,8 @@ class _Scratch:
         key = (device.index, torch.cuda.current_stream(device).cuda_stream)
         buf = self.bufs.get(key)
         if buf is None or buf.numel() < nbytes:
+            if buf is not None and self.keep_outgrown:
+                self.outgrown.append(buf)
             buf = torch.empty(round_up(int(nbytes * 1.25), 512), dtype=torch.uint8, device=device)
             self.bufs[key] = buf
         return C.c_void_p(buf.data_ptr()), buf.numel()
@@ -125,6 +130,56 @@ class _Scratch:
 
 
 scratch = _Scratch()
+
+
+# -------------------------------------------------------------------- epoch
+class EpochProgram:
+    """gcg_epoch (include/gcg.h): the libgcg calls of one f_train recorded once and replayed from C++ -- the
+    counterpart of the compiled ``f_train = theano.function(...)`` of mlpconv.py:265 that mlpconv.py:295 calls
+    once per epoch.  ``with prog.record(): step()`` executes the step AND records it; ``prog.run()`` enqueues the
+    whole epoch on the current stream with one C call (CUDA-graph capturable).  The program owns the scratch
+    its calls use; every other buffer belongs to the model, which must keep it in place (as for a CUDA graph)."""
+
+    def __init__(self):
+        L = _lib.lib()
+        h = C.c_void_p()
+        _lib.check(L.gcg_epoch_create(C.byref(h)), "gcg_epoch_create")
+        self._h = h
+        self._scratch = _Scratch(keep_outgrown=True)
+
+    def record(self):
+        import contextlib
+
+        @contextlib.contextmanager
+        def ctx():
+            global scratch
+            L = _lib.lib()
+            _lib.check(L.gcg_epoch_record_begin(self._h), "gcg_epoch_record_begin")
+            outer, scratch = scratch, self._scratch
+            try:
+                yield self
+            finally:
+                scratch = outer
+                _lib.check(L.gcg_epoch_record_end(self._h), "gcg_epoch_record_end")
+        return ctx()
+
+    def run(self):
+        _lib.check(_lib.lib().gcg_epoch_run(self._h, _stream()), "gcg_epoch_run")
+
+    def __len__(self):
+        return int(_lib.lib().gcg_epoch_size(self._h))
+
+    def call_names(self):
+        L = _lib.lib()
+        return [L.gcg_epoch_call_name(self._h, i).decode() for i in range(len(self))]
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                _lib.lib().gcg_epoch_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
 
 
 # --------------------------------------------------------------------- SpMM

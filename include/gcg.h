@@ -306,6 +306,30 @@ int gcg_elastic_net_f32(int32_t n_tensors, const float* const* h_params, const i
                         const float* h_reg, float* out, void* workspace, int64_t workspace_bytes,
                         void* stream);
 
+/* ------------------------------------------------------------------ epoch */
+
+/* The epoch as one native object.  The reference's epoch is ONE call of a compiled
+ * Theano function: f_train = theano.function([X_sym, y_sym, train_indices_sym], [loss, acc], updates=...)
+ * (mlpconv.py:265), called once per epoch (mlpconv.py:295).  A gcg_epoch is the counterpart of that compiled
+ * object: the ordered list of libgcg calls of one f_train (forward a1-a4/a9, head a10, backward a5-a8, elastic
+ * net + Adam a11-a12), each with its arguments, recorded ONCE from the layer code between
+ * gcg_epoch_record_begin / gcg_epoch_record_end on the calling thread (the calls still execute while being
+ * recorded; host-side tables such as Adam's pointer lists are copied), and replayed by gcg_epoch_run() on the
+ * stream it is given: one C call per epoch, every launch enqueued from C++, CUDA-graph capturable.
+ * The caller keeps every buffer the recorded calls point to alive and unchanged in place (the same rule a CUDA
+ * graph has).  Recorded: every stream-taking compute entry point of this header except the peer-memory ones
+ * (gcg_push_*, gcg_peer_barrier, gcg_spmm_csr_routed_f32 -- their sequence numbers change per call). */
+typedef struct gcg_epoch gcg_epoch;
+int gcg_epoch_create(gcg_epoch** out);
+int gcg_epoch_destroy(gcg_epoch* epoch);
+int gcg_epoch_record_begin(gcg_epoch* epoch);
+int gcg_epoch_record_end(gcg_epoch* epoch);
+/* number of recorded calls, and the entry-point name of call i ("" out of range) */
+int64_t gcg_epoch_size(const gcg_epoch* epoch);
+const char* gcg_epoch_call_name(const gcg_epoch* epoch, int64_t i);
+/* enqueue the recorded calls, in order, on `stream`; stops at the first failing call and returns its status */
+int gcg_epoch_run(const gcg_epoch* epoch, void* stream);
+
 /* --------------------------------------------------------------- host side */
 
 /* k-d tree region labels, bit-exact restatement of kdtree.py:84-118,126-147

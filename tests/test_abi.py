@@ -70,3 +70,22 @@ def test_no_cpu_fallback_in_product_path():
         if fn.endswith(".py"):
             txt = open(os.path.join(ROOT, "graphconvgeo_b200", fn)).read()
             assert "import oracle" not in txt and "from oracle" not in txt, fn
+
+
+def test_epoch_program_object_without_a_gpu():
+    """gcg_epoch_*  bookkeeping needs no device: create / record window / run of an
+    empty program / error statuses and messages."""
+    import ctypes as C
+    from graphconvgeo_b200 import _lib
+    L = _lib.lib()
+    h, h2 = C.c_void_p(), C.c_void_p()
+    assert L.gcg_epoch_create(C.byref(h)) == 0 and L.gcg_epoch_create(C.byref(h2)) == 0
+    assert L.gcg_epoch_size(h) == 0 and L.gcg_epoch_run(h, None) == 0
+    assert L.gcg_epoch_record_begin(h) == 0
+    assert L.gcg_epoch_run(h, None) == -1 and b"still being recorded" in L.gcg_last_error()
+    assert L.gcg_epoch_record_begin(h2) == -1 and b"already recording" in L.gcg_last_error()
+    assert L.gcg_epoch_record_end(h2) == -1
+    assert L.gcg_epoch_record_end(h) == 0 and L.gcg_epoch_run(h, None) == 0
+    assert L.gcg_epoch_call_name(h, 0) == b"" and L.gcg_epoch_call_name(None, 0) == b""
+    assert L.gcg_epoch_create(None) == -1
+    assert L.gcg_epoch_destroy(h) == 0 and L.gcg_epoch_destroy(h2) == 0 and L.gcg_epoch_destroy(None) == 0

@@ -124,6 +124,74 @@ def test_cuda_graph_replay_equals_eager():
     assert a.train_results() == b.train_results()
 
 
+@pytest.mark.parametrize("n_layers,highway,graph", [(2, False, False), (3, True, False), (3, True, True), (4, True, False)])
+def test_native_epoch_program_equals_the_layer_code(n_layers, highway, graph):
+    """the epoch as one native object (gcg_epoch_*, include/gcg.h) -- every libgcg call of
+    f_train recorded once, replayed from C++ with one call per epoch (optionally inside a CUDA graph) -- gives the
+    same parameters, loss and accuracy, bit for bit, as running the layer code call by call from Python."""
+    from graphconvgeo_b200 import ops
+    w = workload()
+    rng = np.random.RandomState(5)
+    params = go.init_params(rng, w.X.shape[1], w.hidden, w.n_classes, n_layers, highway)
+    a = make_model(w, n_layers, highway, params, w.train_indices, cuda_graph=graph)
+    a.native_epoch = True
+    b = make_model(w, n_layers, highway, params, w.train_indices, cuda_graph=False)
+    b.native_epoch = False
+    for step in range(5):
+        a.f_train()
+        b.f_train()
+        torch.cuda.synchronize()
+        assert a.train_results() == b.train_results(), step
+    assert a._program is not None and (a._graph is not None) == graph and b._program is None
+    for pa, pb in zip(a.get_param_values(), b.get_param_values()):
+        assert np.array_equal(pa, pb)
+    names = a._program.call_names()
+    assert len(names) == len(a._program) > 10
+    assert names[-1] == "gcg_adam_step_f32" and "gcg_softmax_ce_f32" in names and "gcg_spmm_csr_f32" in names
+    assert sum(n == "gcg_spmm_csr_f32" for n in names) >= 2 * n_layers        # X.W1, A_hat products, their transposes
+    # one C call enqueues them all: the library's launch counter advances by the same amount as an eager epoch
+    ops.launch_count(reset=True)
+    b.f_train()
+    eager = ops.launch_count(reset=True)
+    if not graph:
+        a.f_train()
+        assert ops.launch_count(reset=True) == eager
+    # evaluation between epochs does not disturb the recorded program
+    va = a.f_val(a.y_dev_dev, a.ti["dev"])
+    vb = b.f_val(b.y_dev_dev, b.ti["dev"])
+    if graph:
+        a.f_train()          # (b took one more step above, for the launch count)
+    a.f_train()
+    b.f_train()
+    torch.cuda.synchronize()
+    assert a.train_results() == b.train_results()
+    assert va[1] == pytest.approx(vb[1])
+
+
+def test_epoch_program_api_errors():
+    from graphconvgeo_b200 import _lib, ops
+    L = _lib.lib()
+    p = ops.EpochProgram()
+    assert len(p) == 0 and p.call_names() == []
+    p.run()                                                     # an empty program is a no-op
+    with p.record():
+        q = ops.EpochProgram()
+        with pytest.raises(_lib.GcgError, match="already recording"):
+            with q.record():
+                pass
+        with pytest.raises(_lib.GcgError, match="still being recorded"):
+            p.run()
+        x = torch.arange(12, dtype=torch.float32, device="cuda")
+        out = torch.zeros(1, dtype=torch.float32, device="cuda")
+        ops.sum_scaled(x, 0.5, out=out)
+    assert p.call_names() == ["gcg_sum_f32"] and float(out.item()) == 33.0
+    x.mul_(2.0)
+    p.run()
+    assert float(out.item()) == 66.0
+    with pytest.raises(_lib.GcgError):
+        _lib.check(L.gcg_epoch_run(None, None), "gcg_epoch_run")
+
+
 def test_fit_learns_and_keeps_the_reference_interface(tmp_path):
     from graphconvgeo_b200.mlpconv import MLPCONV
     w = workload()
