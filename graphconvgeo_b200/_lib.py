@@ -58,6 +58,7 @@ PROTOTYPES = {
     "gcg_sum_slabs_f32": (c_int, [c_vp, c_i32, c_i64, c_vp, c_vp]),
     "gcg_scatter_rows_f32": (c_int, [c_vp, c_i64, c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp]),
     "gcg_gather_rows_f32": (c_int, [c_vp, c_i64, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp]),
+    "gcg_put_rows_f32": (c_int, [c_vp, c_i64, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp]),
     "gcg_pack_cols_f32": (c_int, [c_vp, c_i64, c_i64, c_i64, c_i32, c_i64, c_vp, c_vp]),
     "gcg_unpack_cols_f32": (c_int, [c_vp, c_i64, c_i64, c_i32, c_i64, c_vp, c_i64, c_vp]),
     "gcg_adam_step_f32": (c_int, [c_i32, C.POINTER(c_vp), C.POINTER(c_vp), C.POINTER(c_vp), C.POINTER(c_vp),

@@ -309,6 +309,19 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restric
     *(reinterpret_cast<T*>(out + i * ld_out) + c) = ld(reinterpret_cast<const T*>(X + r * ld_x) + c);
 }
 
+template <int VEC>
+__global__ void __launch_bounds__(256) put_rows_kernel(const float* __restrict__ src, int64_t ld_src,
+                                                       const int32_t* __restrict__ idx, int64_t n_idx,
+                                                       int64_t W, float* __restrict__ dst, int64_t ld_dst) {
+  using T = typename Vec<VEC>::T;
+  const int lane = threadIdx.x & 31;
+  const int64_t i = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (i >= n_idx) return;
+  const int64_t r = __ldg(idx + i);
+  for (int64_t c = lane; c < W; c += 32)
+    *(reinterpret_cast<T*>(dst + r * ld_dst) + c) = ld(reinterpret_cast<const T*>(src + i * ld_src) + c);
+}
+
 // --------------------------------------------------------------------- Adam
 constexpr int kAdamMaxTensors = 32;
 constexpr int kAdamChunk = 4096;  // elements per block
@@ -555,6 +568,21 @@ extern "C" int gcg_gather_rows_f32(const float* X, int64_t ld_x, const int32_t* 
     gather_rows_kernel<4><<<(unsigned)ceil_div(n_idx, 8), 256, 0, st>>>(X, ld_x, idx, n_idx, (C + 3) / 4, out, ld_out);
   else
     gather_rows_kernel<1><<<(unsigned)ceil_div(n_idx, 8), 256, 0, st>>>(X, ld_x, idx, n_idx, C, out, ld_out);
+  GCG_LAUNCH_CHECK();
+  return GCG_OK;
+}
+
+extern "C" int gcg_put_rows_f32(const float* src, int64_t ld_src, const int32_t* idx, int64_t n_idx,
+                                int64_t C, float* dst, int64_t ld_dst, void* stream) {
+  GCG_RECORD("gcg_put_rows_f32", gcg_put_rows_f32(src, ld_src, idx, n_idx, C, dst, ld_dst, s__));
+  GCG_CHECK_ARG(src && idx && dst, "gcg_put_rows_f32: NULL argument");
+  GCG_CHECK_SHAPE(C > 0 && ld_src >= C && ld_dst >= C, "gcg_put_rows_f32: bad leading dimension");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (n_idx == 0) return GCG_OK;
+  if (vec_ok(C, {{src, ld_src}, {dst, ld_dst}}))
+    put_rows_kernel<4><<<(unsigned)ceil_div(n_idx, 8), 256, 0, st>>>(src, ld_src, idx, n_idx, (C + 3) / 4, dst, ld_dst);
+  else
+    put_rows_kernel<1><<<(unsigned)ceil_div(n_idx, 8), 256, 0, st>>>(src, ld_src, idx, n_idx, C, dst, ld_dst);
   GCG_LAUNCH_CHECK();
   return GCG_OK;
 }

@@ -464,6 +464,18 @@ def gather_rows(X, idx, out=None):
     return out
 
 
+def put_rows(src, idx, dst):
+    """dst[idx[i], :] = src[i, :] for distinct ``idx`` (int32 device tensor) -- gcg_put_rows_f32."""
+    sp, lds = _mat(src, "src")
+    dp, ldd = _mat(dst, "dst")
+    n, Cc = idx.numel(), src.shape[1]
+    if src.shape[0] != n or dst.shape[1] != Cc:
+        raise ValueError("put_rows: src is %s for %d indices, dst %s" % (tuple(src.shape), n, tuple(dst.shape)))
+    _lib.check(_lib.lib().gcg_put_rows_f32(sp, lds, _vec(idx, "idx", torch.int32), n, Cc, dp, ldd, _stream()),
+               "gcg_put_rows_f32")
+    return dst
+
+
 def pack_cols(src, P, Fp, dst):
     """[n, F] -> [P, n, Fp] column slices, zero padded (gcg_pack_cols_f32)."""
     sp, ld = _mat(src, "src")

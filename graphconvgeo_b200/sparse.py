@@ -596,8 +596,7 @@ class HeadSplit:
         ops.gemm(self.Xh, dZ, transA=True, out=self._g_head, a_split=self.head_split())
         if reduce is not None:
             reduce(self._g_head).wait()
-        dW.index_copy_(0, self.top, self._g_head)
-        return dW
+        return ops.put_rows(self._g_head, self.top_i32, dW)
 
 
 class BlockedRows:
@@ -678,6 +677,7 @@ class BlockedRows:
             blk.spmm_mode = _os.environ.get("GCG_XT_BLOCK_KERNEL", "gather")
             self.blocks.append(blk)
         self.heavy_dev = torch.from_numpy(self.heavy_ids.astype(np.int64)).to(self.device)
+        self.heavy_i32 = self.heavy_dev.to(torch.int32)
         self._tmp = None
         # ONE matrix of all (document block, heavy row) pieces, block-major: row b*n_heavy + r holds the non-zeros of
         # heavy row r inside document block b.  A single balanced streaming SpMM over it (its spans run block by block,
@@ -744,5 +744,5 @@ class BlockedRows:
         for w in pending:
             w.wait()
         if self.blocks:
-            out.index_copy_(0, self.heavy_dev, self._tmp)      # heavy rows are empty in `light`: plain placement
+            ops.put_rows(self._tmp, self.heavy_i32, out)       # heavy rows are empty in `light`: plain placement
         return out

@@ -233,6 +233,10 @@ int gcg_scatter_rows_f32(const float* G, int64_t ld_g, const int32_t* pos_ptr,
 /* out[i,:] = X[idx[i],:]  (lasagne_layers.py:88) */
 int gcg_gather_rows_f32(const float* X, int64_t ld_x, const int32_t* idx, int64_t n_idx,
                         int64_t C, float* out, int64_t ld_out, void* stream);
+/* dst[idx[i],:] = src[i,:] for DISTINCT idx (the inverse placement of gcg_gather_rows_f32): the rows of
+ * dW1 = X^T.dZ1 (Dot.grad of lasagne_layers.py:26,65) that the dense head block computed, put back in place. */
+int gcg_put_rows_f32(const float* src, int64_t ld_src, const int32_t* idx, int64_t n_idx,
+                     int64_t C, float* dst, int64_t ld_dst, void* stream);
 
 /* Transposes around the feature-sliced multi-GPU propagation (graphconvgeo_b200/dist.py):
  * pack:   src [n_rows, F] (ld)  ->  dst [P][n_rows][Fp], slice q = columns [q*Fp, (q+1)*Fp), zero padded;

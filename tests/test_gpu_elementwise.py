@@ -109,6 +109,18 @@ def test_sum_scatter_gather():
     X = rng.standard_normal((N, C)).astype(np.float32)
     got = ops.gather_rows(to_dev(X), torch.from_numpy(idx).cuda()).cpu().numpy()
     assert np.array_equal(got, X[idx])
+    # put_rows: the inverse placement for distinct indices (aligned and unaligned widths); other rows untouched
+    for Cc in (37, 600):
+        sel = rng.permutation(N)[:123].astype(np.int32)
+        src = rng.standard_normal((len(sel), Cc)).astype(np.float32)
+        base = rng.standard_normal((N, Cc)).astype(np.float32)
+        dst = to_dev(base)
+        ops.put_rows(to_dev(src), torch.from_numpy(sel).cuda(), dst)
+        want = base.copy()
+        want[sel] = src
+        assert np.array_equal(dst.cpu().numpy(), want)
+    with pytest.raises(ValueError):
+        ops.put_rows(to_dev(src), torch.from_numpy(sel[:5]).cuda(), dst)
 
 
 def test_adam_matches_lasagne_adam_oracle():

@@ -92,3 +92,22 @@ def test_benched_configuration_every_operation_within_tolerance(name):
     # the absolute term of the bound swallows the tiny gradients of a mean over ~1M targets: every array must also
     # agree to 1e-3 of its own largest value (tcgen05 3xTF32 chains: ~3e-5; float32 sums of 1.4 M terms: ~1e-5)
     assert rep["max_err_over_ref_max"] <= 1e-3, rep["worst_relative_check"]
+
+
+def test_native_epoch_program_equals_layer_code_at_twitter_us():
+    """The gcg_epoch program (every libgcg call of f_train recorded once, replayed from C++) must
+    cover the Twitter-scale code paths too -- dense head / sparse tail of X, document-blocked X^T.dZ1, shared tf32
+    splits, tcgen05 GEMMs: same loss, accuracy and parameters, bit for bit, as the layer code after 4 epochs.
+    (A torch kernel left on the hot path would be missing from the program and show up here.)"""
+    res = []
+    for native in (False, True):
+        m, wl = build("twitter-us", native_epoch=native)
+        for _ in range(4):
+            m.f_train()
+        torch.cuda.synchronize()
+        assert (m._program is not None) == native
+        res.append((m.train_results(), [float(p.double().sum().item()) for p in m.params],
+                    float(m.params[0].double().abs().sum().item())))
+        del m, wl
+        torch.cuda.empty_cache()
+    assert res[0] == res[1]
