@@ -342,7 +342,7 @@ def run_gpu(args):
     log("[rank %d] workload %s built in %.1fs: %s" % (rank, args.workload, time.time() - t0, wl.meta))
 
     model_kwargs = dict(n_epochs=args.steps, regul_coefs=[1e-6, 1e-6], hidden_layer_size=wl.hidden, drop_out=False,
-                        n_layers=args.layers, highway=bool(args.highway), seed=1, device=dev, cuda_graph=True)
+                        n_layers=args.layers, highway=bool(args.highway), seed=1, device=dev, cuda_graph=not args.no_graph)
     if world > 1:
         from graphconvgeo_b200.dist import DistMLPCONV
         m = DistMLPCONV(partition=args.partition, peer_memory=not args.no_peer_memory, **model_kwargs)
@@ -760,6 +760,9 @@ def main():
     ap.add_argument("--layers", type=int, default=3)
     ap.add_argument("--highway", type=int, default=1)
     ap.add_argument("--random-graph", action="store_true", help="Chung-Lu graph without community structure")
+    ap.add_argument("--no-graph", action="store_true",
+                    help="time the epoch without a CUDA graph (SURVEY 8d config 2: the launch-bound GEOTEXT shape with and "
+                         "without one); with GCG_NATIVE_EPOCH=1 the launches then come from gcg_epoch_run (C++), else from Python")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the sampled-row oracle check of one training step")
     ap.add_argument("--parity-rows", type=int, default=1024)
