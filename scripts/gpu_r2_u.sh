@@ -1,6 +1,7 @@
 #!/bin/bash
 # round-2 call "u": determinism of the World epoch on one box, put_rows vs index_copy_, GEOTEXT configs 1/2, Twitter-US record
 mkdir -p gpurun_out
+timeout 300 python __graft_entry__.py --smoke > gpurun_out/u_smoke.log 2>&1; echo "smoke rc=$?"; tail -3 gpurun_out/u_smoke.log
 B="--no-parity --no-cpu-baseline"
 timeout 600 python bench.py $B > gpurun_out/u_world_a.json 2> gpurun_out/u_world_a.log; echo "world a rc=$?"
 timeout 600 python bench.py $B > gpurun_out/u_world_b.json 2> gpurun_out/u_world_b.log; echo "world b rc=$?"
