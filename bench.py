@@ -451,6 +451,8 @@ def run_gpu(args):
                            else "NCCL all-to-all")) if getattr(m, "partition", "") == "feature" else "row blocks + NCCL all-gather"))
                        if world > 1 else "single GPU",
                        gemm_mode=os.environ.get("GCG_GEMM_MODE", "auto"),
+                       **({"collectives": ("libgcg.so (gcg_comm_*: NCCL bound by the C ABI)" if getattr(m, "collectives", "torch") == "native"
+                                           else "torch.distributed (NCCL)")} if world > 1 else {}),
                        epoch_driver=("gcg_epoch_run (the epoch recorded as a C++ call list, include/gcg.h), captured in a CUDA graph"
                                      if getattr(m, "_program", None) is not None else
                                      ("layer code captured in a CUDA graph" if getattr(m, "_graph", None) is not None

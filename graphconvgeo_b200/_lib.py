@@ -67,6 +67,15 @@ PROTOTYPES = {
     "gcg_adam_workspace_bytes": (c_i64, [c_i32, C.POINTER(c_i64)]),
     "gcg_elastic_net_f32": (c_int, [c_i32, C.POINTER(c_vp), C.POINTER(c_i64), C.POINTER(c_f32), c_vp, c_vp,
                                     c_i64, c_vp]),
+    "gcg_comm_unique_id": (c_int, [c_vp]),
+    "gcg_comm_init": (c_int, [c_vp, c_i32, c_i32, C.POINTER(c_vp)]),
+    "gcg_comm_destroy": (c_int, [c_vp]),
+    "gcg_comm_info": (c_int, [c_vp, C.POINTER(c_i32), C.POINTER(c_i32)]),
+    "gcg_comm_wait": (c_int, [c_vp, c_vp]),
+    "gcg_allgather_rows_f32": (c_int, [c_vp, c_vp, c_i64, c_i32, c_vp]),
+    "gcg_allreduce_grads_f32": (c_int, [c_vp, c_i32, C.POINTER(c_vp), C.POINTER(c_i64), c_i32, c_vp]),
+    "gcg_spmm_rowpart_allgather_f32": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp, c_int,
+                                               c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_i32, c_vp, c_i64, c_vp]),
     "gcg_epoch_create": (c_int, [C.POINTER(c_vp)]),
     "gcg_epoch_destroy": (c_int, [c_vp]),
     "gcg_epoch_record_begin": (c_int, [c_vp]),

@@ -21,11 +21,18 @@ OBJ = os.path.join(HERE, "_obj")
 LIB = os.path.join(HERE, "libgcg.so")
 
 SOURCES = ["gcg_core.cu", "gcg_spmm.cu", "gcg_spmm_stream.cu", "gcg_gemm.cu", "gcg_gemm_tc.cu", "gcg_elementwise.cu",
-           "gcg_graph.cu", "gcg_host.cpp", "gcg_peer.cu", "gcg_spgemm.cu"]
+           "gcg_graph.cu", "gcg_host.cpp", "gcg_peer.cu", "gcg_spgemm.cu", "gcg_comm.cu"]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-O3,-Wall,-fopenmp", "--expt-relaxed-constexpr",
               "-I", INCLUDE, "-I", CSRC]
+# nccl.h (types only: gcg_comm.cu binds NCCL with dlopen at run time): the system header, else the wheel's copy
+for _d in ("/usr/include", os.path.join(os.path.dirname(os.path.dirname(sys.executable)), "lib",
+                                        "python%d.%d" % sys.version_info[:2], "site-packages", "nvidia", "nccl", "include")):
+    if os.path.exists(os.path.join(_d, "nccl.h")):
+        if _d != "/usr/include":
+            NVCC_FLAGS += ["-I", _d]
+        break
 
 
 def _nvcc():
@@ -72,7 +79,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     with cf.ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
         objs = list(ex.map(compile_one, srcs))
-    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + ["-Xcompiler", "-fopenmp"]
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + ["-Xcompiler", "-fopenmp", "-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))

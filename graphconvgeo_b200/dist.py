@@ -26,6 +26,92 @@ from .mlpconv import MLPCONV
 from .sparse import CSRMatrix, as_csr
 
 
+class NativeComm:
+    """gcg_comm (include/gcg.h): the collectives of the row-partitioned epoch issued from libgcg.so itself -- NCCL
+    bound at run time, its own communication stream, event fences instead of Work handles.  torch.distributed is
+    only used to hand rank 0's NCCL unique id to the other ranks."""
+
+    class _Fence:
+        def __init__(self, comm):
+            self.comm = comm
+
+        def wait(self):
+            self.comm.wait()
+
+    def __init__(self, group=None):
+        import ctypes as C
+        from . import _lib
+        Lb = _lib.lib()
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        uid = C.create_string_buffer(128)
+        if self.rank == 0:
+            _lib.check(Lb.gcg_comm_unique_id(uid), "gcg_comm_unique_id")
+        box = [bytes(uid.raw)]
+        dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        self._uid = C.create_string_buffer(box[0], 128)
+        h = C.c_void_p()
+        _lib.check(Lb.gcg_comm_init(self._uid, self.world, self.rank, C.byref(h)), "gcg_comm_init")
+        self._h = h
+
+    def wait(self):
+        from . import _lib
+        _lib.check(_lib.lib().gcg_comm_wait(self._h, ops._stream()), "gcg_comm_wait")
+
+    def all_reduce(self, tensors, wait=False):
+        """in-place sum over ranks of contiguous float32 tensors (one NCCL group); returns a fence with wait()"""
+        import ctypes as C
+        from . import _lib
+        ts = [t for t in (tensors if isinstance(tensors, (list, tuple)) else [tensors])]
+        for t in ts:
+            if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+                raise TypeError("NativeComm.all_reduce needs contiguous float32 CUDA tensors")
+        n = len(ts)
+        ptrs = (C.c_void_p * max(n, 1))(*[t.data_ptr() for t in ts])
+        sizes = (C.c_int64 * max(n, 1))(*[t.numel() for t in ts])
+        _lib.check(_lib.lib().gcg_allreduce_grads_f32(self._h, n, ptrs, sizes, int(bool(wait)), ops._stream()),
+                   "gcg_allreduce_grads_f32")
+        return NativeComm._Fence(self)
+
+    def all_gather(self, full, floats_per_rank, wait=True):
+        """in-place all-gather of ``full`` = [world][floats_per_rank] (gcg_allgather_rows_f32)"""
+        import ctypes as C
+        from . import _lib
+        _lib.check(_lib.lib().gcg_allgather_rows_f32(self._h, C.c_void_p(full.data_ptr()), int(floats_per_rank),
+                                                     int(bool(wait)), ops._stream()), "gcg_allgather_rows_f32")
+        return NativeComm._Fence(self)
+
+    def spmm_rowpart(self, diag, off, full, F, n_loc, out, **epi):
+        """gcg_spmm_rowpart_allgather_f32: in-place all-gather of ``full`` ([world*n_loc, ld] buffer, F <= ld valid
+        columns) overlapped with the diagonal block"""
+        from . import _lib
+        fp, ld = ops._mat(full, "Z_full")
+        cp, ldc = ops._mat(out, "out")
+        gate, carry, conv = epi.get("gate"), epi.get("carry"), epi.get("conv_out")
+        gp = hp = vp = None
+        ldg = ldh = ldv = 0
+        if gate is not None:
+            gp, ldg = ops._mat(gate, "gate")
+            hp, ldh = ops._mat(carry, "carry")
+            if conv is not None:
+                vp, ldv = ops._mat(conv, "conv_out")
+        ws, wsb = ops.scratch.get(max(diag.workspace_bytes(ldc), off.workspace_bytes(ldc)), full.device)
+        pc = ops.auto_panel_cols(off.shape[1], F, off.nnz, getattr(off, "spmm_mode", None))
+        _lib.check(_lib.lib().gcg_spmm_rowpart_allgather_f32(
+            self._h, diag.plan, off.plan, fp, ld, F, int(n_loc), cp, ldc, ops._vec(epi.get("bias"), "bias"),
+            _lib.act_code(epi.get("act", "identity")), gp, ldg, hp, ldh, vp, ldv, int(pc), ws, wsb, ops._stream()),
+            "gcg_spmm_rowpart_allgather_f32")
+        return out
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                from . import _lib
+                _lib.lib().gcg_comm_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+
 class RowPartition:
     """Equal contiguous row blocks (padded): n_loc = ceil(N / P) rounded up to 4 rows."""
 
@@ -39,6 +125,7 @@ class RowPartition:
         self.group = group
         self._full = {}
         self.bytes_gathered = 0
+        self.comm = None            # NativeComm: collectives through the C ABI instead of torch.distributed
 
     def owner(self, rows):
         return np.asarray(rows) // self.n_loc
@@ -144,9 +231,18 @@ class DistCSRMatrix:
         if full is None:
             full = part.full(key, F)
             part.local_view(full).copy_(B)
-        work = part.all_gather_async(full)                # NCCL stream; waits for what is enqueued so far
         if out is None:
             out = ops.alloc_mat(self.shape[0], F, B.device)
+        base = full._base if full._base is not None else full
+        if part.comm is not None:
+            assert base.is_contiguous() and base.shape[0] == part.n_pad
+            part.bytes_gathered += (part.world - 1) * part.n_loc * base.stride(0) * 4
+            if self.shape[0] == 0:      # no rows here (a rank without targets): still a party to the collective
+                part.comm.all_gather(base, part.n_loc * base.stride(0))
+                return out
+            # the whole propagation (gather, diagonal block, fence, off-diagonal block + epilogue) is ONE C call
+            return part.comm.spmm_rowpart(self.diag, self.off, base, F, part.n_loc, out, **epi)
+        work = part.all_gather_async(full)                # NCCL stream; waits for what is enqueued so far
         if self.shape[0] > 0:
             ops.spmm(self.diag, full, out=out)            # local columns: only the local slab is read
         work.wait()                                       # main stream waits for the gather
@@ -467,7 +563,7 @@ class DistMLPCONV(MLPCONV):
     single-process fit() is); each keeps its row block.  Results (loss, acc, predictions gathered
     over ranks, parameters) equal the single-GPU ones up to summation order of the all-reduces."""
 
-    def __init__(self, *args, group=None, partition="auto", peer_memory=True, **kwargs):
+    def __init__(self, *args, group=None, partition="auto", peer_memory=True, collectives=None, **kwargs):
         kwargs["cuda_graph"] = False          # NCCL work is enqueued eagerly
         kwargs["native_epoch"] = False        # collectives and peer barriers are not part of a gcg_epoch
         super().__init__(*args, **kwargs)
@@ -479,6 +575,11 @@ class DistMLPCONV(MLPCONV):
         self.group = group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
+        # "torch": torch.distributed issues the collectives; "native": libgcg.so does (gcg_comm_*, gcg_allreduce_grads_f32,
+        # gcg_spmm_rowpart_allgather_f32 -- the survey's multi-GPU C ABI).  Same NCCL underneath.
+        import os
+        self.collectives = collectives or os.environ.get("GCG_DIST_COMM", "torch")
+        assert self.collectives in ("torch", "native")
 
     def prepare(self, X, train_indices, dev_indices, test_indices, Y, H):
         Y = np.asarray(Y)
@@ -510,6 +611,9 @@ class DistMLPCONV(MLPCONV):
         self._node_map = node_map
         part = RowPartition(n, self.world, self.rank, self.device, self.group)
         self.part = part
+        if self.collectives == "native":
+            with torch.cuda.device(self.device):
+                part.comm = NativeComm(self.group)
         Hd = (FeatureSplitCSRMatrix if self.partition == "feature" else DistCSRMatrix).from_global(Hg, part)
         part.peer = None
         if self.partition == "feature" and self.peer_memory and self.world > 1:
@@ -593,23 +697,33 @@ class DistMLPCONV(MLPCONV):
         n, C = logits.shape
         G = self.l_out._mat("G", n, C)
         hb = self._head(logits, y, ti.n_global, grad=G)
-        works = [dist.all_reduce(hb["out"], group=self.group, async_op=True)]
+        works = [self._all_reduce_async(hb["out"])]
         self._backward(G, works)          # each layer's gradient all-reduce starts as soon as it is computed
         for w in works:
             w.wait()
         self.adam.step()
         self._train_hb = hb
 
+    def _all_reduce_async(self, t):
+        """sum over ranks, in place; returns a handle with wait() (a torch Work, or a fence of the native communicator)"""
+        comm = self.part.comm
+        if comm is not None and t.dtype == torch.float32 and t.is_contiguous():
+            return comm.all_reduce(t)
+        return dist.all_reduce(t, group=self.group, async_op=True)
+
     def _backward(self, G, works=None):
         def reduce_grads(ly):
             if works is not None:
-                for k, g in ly.grads.items():
-                    if k == "W" and getattr(ly, "_grad_reduce", None) is not None:
-                        continue          # already summed piece by piece inside the X^T.dZ1 product
-                    works.append(dist.all_reduce(g, group=self.group, async_op=True))
+                gs = [g for k, g in ly.grads.items()
+                      if not (k == "W" and getattr(ly, "_grad_reduce", None) is not None)]   # dW1: summed piece by piece
+                comm = self.part.comm                                                        # inside the X^T.dZ1 product
+                if comm is not None and gs and all(g.is_contiguous() for g in gs):
+                    works.append(comm.all_reduce(gs))          # the layer's gradients in one NCCL group
+                else:
+                    works.extend(self._all_reduce_async(g) for g in gs)
         # dW1 = X^T.dZ1 is the largest message of the epoch (V x h floats) and the last gradient to be computed:
         # its pieces are all-reduced as they are finished, overlapped with the rest of the product
-        self.l_hid1._grad_reduce = (lambda t: dist.all_reduce(t, group=self.group, async_op=True)) if works is not None else None
+        self.l_hid1._grad_reduce = self._all_reduce_async if works is not None else None
         from .mlpconv import DropoutLayer
         grad, preact = G, False
         for i in range(len(self.layers) - 1, -1, -1):

@@ -25,6 +25,13 @@ import torch
 from . import ops
 from .sparse import CSRMatrix, as_csr, is_sparse
 
+# Forward projections H.W of the hidden layers on the tensor-core engine keep their accumulation chains short
+# (GCG_GEMM_TF32X3_CHAINED, as the logits product does): after ~25 epochs the hidden activations of the Twitter
+# shapes reach ~16 and the one-chain product sat at 1.14x the parity bound on 2 of 614,400 sampled values
+# (profiles/r02_parity_notes.md); the gate product feeds a sigmoid and stays as it was (0.08x).  0 switches it off.
+import os as _os
+_FWD_CHAINED = _os.environ.get("GCG_FWD_CHAINED", "1") != "0"
+
 # --------------------------------------------------------------------------- #
 # lasagne.nonlinearities / lasagne.init look-alikes                            #
 # --------------------------------------------------------------------------- #
@@ -511,7 +518,7 @@ class ConvolutionDenseLayer(_ConvBase):
             return self._forward_propagate_first(input, ti, kwargs)
         self._s_in = self._split("in", input, self.num_units)
         z = ops.gemm(input, self.W, out=self._operand("Z", N, self.num_units), a_split=self._s_in,
-                     chained=(self.nonlinearity == "softmax"))                              # :82
+                     chained=_FWD_CHAINED or self.nonlinearity == "softmax")                # :82
         Hm = self.H if ti is None else ti.Hsub
         n_out = N if ti is None else ti.n
         fused_act = "identity" if self.nonlinearity == "softmax" else self.nonlinearity
@@ -577,7 +584,7 @@ class HighwayConvolutionDenseLayer(ConvolutionDenseLayer):
         N, h = input.shape[0], self.num_units
         self._in = input
         self._s_in = self._split("in", input, h)                  # one hi/lo split feeds four GEMMs (fwd 2, bwd 2)
-        z = ops.gemm(input, self.W, out=self._operand("Z", N, h), a_split=self._s_in)
+        z = ops.gemm(input, self.W, out=self._operand("Z", N, h), a_split=self._s_in, chained=_FWD_CHAINED)
         g = ops.gemm(input, self.Wg, bias=self.bg, act="sigmoid", out=self._mat("g", N, h), a_split=self._s_in)
         conv = self._mat("Hc", N, h) if kwargs.get("train", False) else None
         out = ops.spmm(self.H, z, bias=self.b, act=self.nonlinearity, gate=g, carry=input, conv_out=conv,

@@ -76,7 +76,7 @@ class MLPCONV:
         self.seed = seed
         self.cuda_graph = cuda_graph
         # the epoch as a native gcg_epoch object (see f_train); None = the GCG_NATIVE_EPOCH environment switch
-        self.native_epoch = (os.environ.get("GCG_NATIVE_EPOCH", "0") != "0") if native_epoch is None else bool(native_epoch)
+        self.native_epoch = (os.environ.get("GCG_NATIVE_EPOCH", "1") != "0") if native_epoch is None else bool(native_epoch)
         self.model_dir = model_dir
         self.learning_rate = learning_rate
         self.reorder = reorder      # None | "auto" | "labels" | "degree" | explicit permutation (new -> old)

@@ -310,6 +310,38 @@ int gcg_elastic_net_f32(int32_t n_tensors, const float* const* h_params, const i
                         const float* h_reg, float* out, void* workspace, int64_t workspace_bytes,
                         void* stream);
 
+/* -------------------------------------------------- multi-GPU (NCCL over NVLink) */
+
+/* One process per GPU, A_hat row-partitioned (the reference is single-process).  NCCL is bound
+ * at run time (dlopen of libnccl.so.2: inside a PyTorch process the copy torch already loaded), so single-GPU users
+ * of this library never touch it.  The unique id is made on rank 0 (gcg_comm_unique_id, 128 bytes) and handed to
+ * the other ranks by the launcher's own means (the Python shim broadcasts it with torch.distributed). */
+typedef struct gcg_comm gcg_comm;
+int gcg_comm_unique_id(void* id128);
+/* collective over all ranks; binds the communicator to the CURRENT device and creates its communication stream */
+int gcg_comm_init(const void* id128, int32_t world, int32_t rank, gcg_comm** out);
+int gcg_comm_destroy(gcg_comm* comm);
+int gcg_comm_info(const gcg_comm* comm, int32_t* world, int32_t* rank);
+/* `stream` waits for every collective issued so far on the communicator (no host synchronisation) */
+int gcg_comm_wait(gcg_comm* comm, void* stream);
+/* in-place all-gather of `full` = [world][floats_per_rank]: slab `rank` is this rank's contribution; starts when the
+ * work already enqueued on `stream` is done; wait != 0: `stream` also waits for the result (else gcg_comm_wait) */
+int gcg_allgather_rows_f32(gcg_comm* comm, float* full, int64_t floats_per_rank, int32_t wait, void* stream);
+/* sum over ranks, in place, of n_tensors gradient buffers in one NCCL group (theano.grad of a loss that is a mean
+ * over ALL targets, mlpconv.py:230,263: each rank holds the partial sum over its rows); wait as above */
+int gcg_allreduce_grads_f32(gcg_comm* comm, int32_t n_tensors, float* const* h_bufs, const int64_t* h_sizes,
+                            int32_t wait, void* stream);
+/* One propagation S.dot(H, Z) (lasagne_layers.py:67,84) for the row block of this rank -- north_star's design:
+ * Z_full = [world*n_loc, ld] holds this rank's slab at rows [rank*n_loc, (rank+1)*n_loc); it is all-gathered in place
+ * on the communication stream WHILE `stream` runs C = diag . Z_full (`diag`: the columns of the local slab), then
+ * C = epilogue(C + off . Z_full) (`off`: all other columns) once the gather has landed.  Both plans are
+ * [n_rows_local x world*n_loc]; epilogue arguments as in gcg_spmm_csr_f32. */
+int gcg_spmm_rowpart_allgather_f32(gcg_comm* comm, const gcg_plan* diag, const gcg_plan* off, float* Z_full,
+                                   int64_t ld, int64_t F, int64_t n_loc, float* C, int64_t ldc,
+                                   const float* bias, int act, const float* gate, int64_t ld_gate,
+                                   const float* carry, int64_t ld_carry, float* conv_out, int64_t ld_conv,
+                                   int32_t panel_cols, void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------ epoch */
 
 /* The epoch as one native object.  The reference's epoch is ONE call of a compiled

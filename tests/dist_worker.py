@@ -33,8 +33,14 @@ def gpu_main():
             (3, True, None, "row", False, True), (2, False, "labels", "feature", True, True),
             # Twitter-scale code paths forced on the small input: dense head of X on the tensor-core engine, document-
             # blocked X^T.dZ1, dW1 summed over ranks piece by piece (the pieces must mean the same on every rank)
-            (3, True, "labels", "feature", True, "big"), (2, False, None, "row", False, "big")]
-    for n_layers, highway, reorder, partition, peer, drop in cases:
+            (3, True, "labels", "feature", True, "big"), (2, False, None, "row", False, "big"),
+            # the collectives issued from libgcg.so itself (gcg_comm_init, gcg_spmm_rowpart_allgather_f32,
+            # gcg_allreduce_grads_f32: the multi-GPU C ABI of SURVEY section 8b) instead of torch.distributed
+            (3, True, "labels", "row", False, False, "native"), (2, False, None, "row", False, "big", "native"),
+            (3, True, None, "feature", True, False, "native")]
+    for case in cases:
+        n_layers, highway, reorder, partition, peer, drop = case[:6]
+        collectives = case[6] if len(case) > 6 else "torch"
         big = drop == "big"
         drop = drop is True
         os.environ["GCG_X_FORCE_BIG"] = "1" if big else "0"
@@ -53,9 +59,10 @@ def gpu_main():
         hist = go.train_epochs(net, ref_params, idx, y, 3)
         m = DistMLPCONV(n_epochs=1, regul_coefs=[1e-4, 2e-4], hidden_layer_size=w.hidden, n_layers=n_layers,
                         highway=highway, init_parameters=[p.copy() for p in params], device=dev, reorder=reorder,
-                        partition=partition, peer_memory=peer, drop_out=drop, dropout_coefs=[0.0, 0.0])
+                        partition=partition, peer_memory=peer, drop_out=drop, dropout_coefs=[0.0, 0.0],
+                        collectives=collectives)
         m.prepare(w.X, idx, w.dev_indices, w.test_indices, w.Y, w.A_hat)
-        assert m.part.world == world
+        assert m.part.world == world and (m.part.comm is not None) == (collectives == "native")
         for step in range(3):
             m.f_train()
             l, a = m.train_results()
@@ -86,7 +93,8 @@ def gpu_main():
         assert abs(acc - ref_acc) <= 2.0 / len(w.test_indices)
         if rank == 0:
             print("dist case", n_layers, highway, reorder, partition, "peer" if (peer and m.part.peer is not None) else "nccl",
-                  "dropout(p=0)" if drop else "", "forced Twitter-scale paths" if big else "", "OK", flush=True)
+                  "dropout(p=0)" if drop else "", "forced Twitter-scale paths" if big else "",
+                  "collectives: " + collectives, "OK", flush=True)
         if m.part.peer is not None:
             m.part.peer.check()
     dist.barrier()

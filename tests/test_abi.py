@@ -89,3 +89,22 @@ def test_epoch_program_object_without_a_gpu():
     assert L.gcg_epoch_call_name(h, 0) == b"" and L.gcg_epoch_call_name(None, 0) == b""
     assert L.gcg_epoch_create(None) == -1
     assert L.gcg_epoch_destroy(h) == 0 and L.gcg_epoch_destroy(h2) == 0 and L.gcg_epoch_destroy(None) == 0
+
+
+def test_multi_gpu_entry_points_check_their_arguments():
+    """gcg_comm_* / gcg_allreduce_grads_f32 / gcg_spmm_rowpart_allgather_f32: argument errors are
+    reported before NCCL or CUDA are touched (NCCL is only bound, by dlopen, inside gcg_comm_unique_id / _init)."""
+    import ctypes as C
+    from graphconvgeo_b200 import _lib
+    L = _lib.lib()
+    h = C.c_void_p()
+    assert L.gcg_comm_init(None, 2, 0, C.byref(h)) == -1 and b"NULL" in L.gcg_last_error()
+    uid = C.create_string_buffer(128)
+    assert L.gcg_comm_init(uid, 2, 2, C.byref(h)) == -1 and b"rank 2 of 2" in L.gcg_last_error()
+    assert L.gcg_comm_unique_id(None) == -1
+    assert L.gcg_comm_wait(None, None) == -1
+    assert L.gcg_allreduce_grads_f32(None, 0, None, None, 1, None) == -1
+    assert L.gcg_allgather_rows_f32(None, None, 0, 1, None) == -1
+    assert L.gcg_spmm_rowpart_allgather_f32(None, None, None, None, 0, 0, 0, None, 0, None, 0, None, 0, None, 0, None, 0,
+                                            0, None, 0, None) == -1
+    assert L.gcg_comm_destroy(None) == 0

@@ -115,6 +115,7 @@ def test_cuda_graph_replay_equals_eager():
     params = go.init_params(rng, w.X.shape[1], w.hidden, w.n_classes, 3, True)
     a = make_model(w, 3, True, params, w.train_indices, cuda_graph=True)
     b = make_model(w, 3, True, params, w.train_indices, cuda_graph=False)
+    a.native_epoch = b.native_epoch = False     # the layer code itself, captured vs eager (the native epoch: next test)
     for _ in range(4):
         a.f_train()
         b.f_train()
