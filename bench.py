@@ -292,6 +292,8 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if args.random_graph:
+        raise SystemExit("--impl reference runs the community graph (the benched configuration) only")
     ms, desc, threads, n_timed, n_warm, meta = cpu_reference_epochs(args.workload, args.layers, bool(args.highway),
                                                                      args.steps, args.warmup)
     line = {
@@ -299,7 +301,9 @@ def run_reference(args):
         "steps": n_timed, "warmup": n_warm, "ms_per_step": ms, "higher_is_better": False,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": dict(bench_config(args), nodes=meta["n"], vocab=meta["vocab"], hidden=meta["hidden"],
-                       regions=meta["regions"], nnz_A=meta["nnz_A"], nnz_X=meta["nnz_X"], max_degree=meta["max_degree"]),
+                       regions=meta["regions"], nnz_A=meta["nnz_A"], nnz_X=meta["nnz_X"], max_degree=meta["max_degree"],
+                       graph="community"),
+        "engine": {"parallelism": "host: scipy csr@dense on 1 thread (as under Theano) + BLAS on %d threads" % threads},
         "cpu_baseline": {"value": ms, "unit": "ms", "cores": threads, "kind": "port", "sample": desc},
         "e2e": {"value": ms, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -443,10 +447,12 @@ def run_gpu(args):
         "metric": "gcn_fwd_bwd_epoch_ms", "value": ms_per_step, "unit": "ms", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": False, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        # `config` names the WORKLOAD only and is identical, key for key, in the reference arm's line (the driver
+        # compares the two); how this arm executes it is in `engine`
         "config": dict(bench_config(args), nodes=wl.meta["n"], vocab=wl.meta["vocab"], hidden=wl.hidden,
                        regions=wl.n_classes, nnz_A=wl.meta["nnz_A"], nnz_X=wl.meta["nnz_X"],
-                       max_degree=wl.meta["max_degree"], graph="community" if wl.meta["community"] else "chung-lu",
-                       parallelism=("rows x%d, A_hat.Z %s" % (world, ("feature-sliced, transposes by %s" % (
+                       max_degree=wl.meta["max_degree"], graph="community" if wl.meta["community"] else "chung-lu"),
+        "engine": dict(parallelism=("rows x%d, A_hat.Z %s" % (world, ("feature-sliced, transposes by %s" % (
                            "peer-memory stores over NVLink" if getattr(getattr(m, "part", None), "peer", None) is not None
                            else "NCCL all-to-all")) if getattr(m, "partition", "") == "feature" else "row blocks + NCCL all-gather"))
                        if world > 1 else "single GPU",

@@ -9,7 +9,7 @@ python - <<'PY'
 import json
 a = json.loads(open("gpurun_out/s_bench_native.json").read().strip().splitlines()[-1])
 b = json.loads(open("profiles/r02_bench_default_world.json").read().strip().splitlines()[-1])
-print("native: value %.2f e2e %.2f loss %r acc %r driver %s" % (a["value"], a["e2e"]["value"], a["loss"], a["acc"], a["config"].get("epoch_driver")))
+print("native: value %.2f e2e %.2f loss %r acc %r driver %s" % (a["value"], a["e2e"]["value"], a["loss"], a["acc"], a.get("engine", a["config"]).get("epoch_driver")))
 print("python: value %.2f e2e %.2f loss %r acc %r" % (b["value"], b["e2e"]["value"], b["loss"], b["acc"]))
 print("same loss/acc bits:", a["loss"] == b["loss"] and a["acc"] == b["acc"], "launches", a["launches_per_epoch"], b["launches_per_epoch"])
 PY

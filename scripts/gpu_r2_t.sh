@@ -11,8 +11,8 @@ python - <<'PY'
 import json
 a = json.loads(open("gpurun_out/t_bench_native.json").read().strip().splitlines()[-1])
 b = json.loads(open("gpurun_out/t_bench_default.json").read().strip().splitlines()[-1])
-print("native: value %.2f e2e %.2f loss %r acc %r driver %s" % (a["value"], a["e2e"]["value"], a["loss"], a["acc"], a["config"].get("epoch_driver")))
-print("python: value %.2f e2e %.2f loss %r acc %r driver %s" % (b["value"], b["e2e"]["value"], b["loss"], b["acc"], b["config"].get("epoch_driver")))
+print("native: value %.2f e2e %.2f loss %r acc %r driver %s" % (a["value"], a["e2e"]["value"], a["loss"], a["acc"], a.get("engine", a["config"]).get("epoch_driver")))
+print("python: value %.2f e2e %.2f loss %r acc %r driver %s" % (b["value"], b["e2e"]["value"], b["loss"], b["acc"], b.get("engine", b["config"]).get("epoch_driver")))
 print("same loss/acc bits:", a["loss"] == b["loss"] and a["acc"] == b["acc"], "launches", a["launches_per_epoch"], b["launches_per_epoch"])
 p = b.get("parity", {})
 print("parity", p.get("max_scaled_err"), p.get("worst_check"), p.get("checks_over_tolerance"), p.get("reference_f32_noise"))

@@ -23,7 +23,7 @@ import json, glob
 for f in sorted(glob.glob("gpurun_out/u_*.json")):
     try:
         d = json.loads(open(f).read().strip().splitlines()[-1])
-        print("%-48s value %10.3f e2e %10.3f loss %r acc %r %s" % (f.split("/")[-1], d["value"], d.get("e2e", {}).get("value", -1), d.get("loss"), d.get("acc"), d["config"].get("epoch_driver", "")[:40]))
+        print("%-48s value %10.3f e2e %10.3f loss %r acc %r %s" % (f.split("/")[-1], d["value"], d.get("e2e", {}).get("value", -1), d.get("loss"), d.get("acc"), d.get("engine", d["config"]).get("epoch_driver", "")[:40]))
         if "parity" in d:
             print("      parity", d["parity"]["max_scaled_err"], d["parity"]["worst_check"], d["parity"].get("max_scaled_err_over_reference_noise"))
     except Exception as e:

@@ -12,7 +12,7 @@ import json, glob
 for f in sorted(glob.glob("gpurun_out/v_bench_*.json")):
     d = json.loads(open(f).read().strip().splitlines()[-1])
     p = d.get("parity", {})
-    print("%-28s value %8.3f e2e %8.3f frac %.4f loss %r driver %s" % (f.split("/")[-1], d["value"], d["e2e"]["value"], d["roofline"]["frac"], d["loss"], d["config"].get("epoch_driver", "")[:30]))
+    print("%-28s value %8.3f e2e %8.3f frac %.4f loss %r driver %s" % (f.split("/")[-1], d["value"], d["e2e"]["value"], d["roofline"]["frac"], d["loss"], d.get("engine", d["config"]).get("epoch_driver", "")[:30]))
     print("    parity max %.3f (%s) over-noise %.3f over: %s" % (p.get("max_scaled_err", -1), p.get("worst_check"), p.get("max_scaled_err_over_reference_noise", -1), p.get("checks_over_tolerance")))
     print("    noise", p.get("reference_f32_noise"))
 PY

@@ -11,7 +11,7 @@ for f in sorted(glob.glob("gpurun_out/w_bench_g2_*.json")):
     try:
         d = json.loads(open(f).read().strip().splitlines()[-1])
         p = d.get("parity", {})
-        print("%-28s value %8.3f e2e %8.3f loss %r %s | %s" % (f.split("/")[-1], d["value"], d["e2e"]["value"], d["loss"], d["config"].get("parallelism"), d["config"].get("collectives")))
+        print("%-28s value %8.3f e2e %8.3f loss %r %s | %s" % (f.split("/")[-1], d["value"], d["e2e"]["value"], d["loss"], d.get("engine", d["config"]).get("parallelism"), d.get("engine", d["config"]).get("collectives")))
         print("    parity max %.3f (%s) over-noise %.3f" % (p.get("max_scaled_err", -1), p.get("worst_check"), p.get("max_scaled_err_over_reference_noise", -1)))
     except Exception as e:
         print(f, "unreadable", e)
