@@ -50,6 +50,12 @@ struct StreamState {
 
 static int g_stream_variant = 0;     // 0 = auto
 static int g_stream_span_nnz = 0;    // 0 = default
+// Non-zeros per span (= per warp).  All 148 x 16 warps advance together, so the rows whose neighbourhoods compete for
+// L2 at any moment are the span length times 2,368: SHORT spans keep that window narrow.  An LRU model of the benched
+// graph (scripts/l2_model.py, profiles/r02_l2_model.json) reproduces the measured traffic at 256 (47.7 GB modelled,
+// 49.6 GB measured) and at 384 (51.9 GB; 8.30 vs 7.65 ms measured = the same ratio) and predicts 42 / 38.7 GB at
+// 128 / 64; the per-span start-up (two dependent loads + 4 pipeline-fill iterations) bounds it from below.
+constexpr int kDefaultSpanNnz = 384;
 static int g_stream_near = -1;       // -1 = plan's own choice, 0 = every gather evict_last, > 0 = window in rows
 
 void stream_state_destroy(StreamState* s) {
@@ -456,8 +462,10 @@ int spmm_stream_launch(const gcg_plan* p, SpmmArgs& a, cudaStream_t st) {
   // default span: 384 non-zeros, shorter for small matrices so that the grid still covers the 148 SMs twice over
   int span_nnz = g_stream_span_nnz;
   if (span_nnz <= 0) {
+    static const int env_span = getenv("GCG_STREAM_SPAN") ? atoi(getenv("GCG_STREAM_SPAN")) : 0;
     const int64_t nz = (int64_t)p->h_indptr[p->n_rows] - p->h_indptr[0];
-    span_nnz = (int)std::min<int64_t>(384, std::max<int64_t>(32, nz / (kNumSMs * 16 * 2)));
+    span_nnz = (int)std::min<int64_t>(env_span > 0 ? env_span : kDefaultSpanNnz,
+                                      std::max<int64_t>(32, nz / (kNumSMs * 16 * 2)));
   }
   StreamSchedule sched;
   {
