@@ -56,6 +56,7 @@ static int g_stream_span_nnz = 0;    // 0 = default
 // 49.6 GB measured) and at 384 (51.9 GB; 8.30 vs 7.65 ms measured = the same ratio) and predicts 42 / 38.7 GB at
 // 128 / 64; the per-span start-up (two dependent loads + 4 pipeline-fill iterations) bounds it from below.
 constexpr int kDefaultSpanNnz = 384;
+constexpr int kStreamPersistent = 0;   // 1: one CTA per SM, warps loop over the spans (see spmm_stream_body)
 static int g_stream_near = -1;       // -1 = plan's own choice, 0 = every gather evict_last, > 0 = window in rows
 
 void stream_state_destroy(StreamState* s) {
@@ -143,12 +144,17 @@ __device__ __forceinline__ void spmm_stream_body(const SpmmArgs& a, const Stream
                                                  int warps_per_cta, int near_window) {
   extern __shared__ __align__(128) uint8_t smem_dyn[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int si = blockIdx.x * warps_per_cta + warp;
-  if (si >= n_spans) return;
-  const int4 spv = __ldg(reinterpret_cast<const int4*>(spans) + si);
-  const int v_beg = spv.x, v_end = spv.y, f4_beg = spv.z, f4_cnt = spv.w;
   const uint64_t keep = policy_evict_last(), strm = policy_evict_first();
   const unsigned full = 0xffffffffu;
+  // Grid-stride over the spans: with a PERSISTENT grid (one CTA per SM, spmm_stream_launch) warp w runs spans
+  // w, w + G, w + 2G, ... (G = warps of the grid), so the spans in flight are still G consecutive ones -- the L2
+  // window of the schedule -- but a warp that finishes a span starts its next one while the other 15 warps of the
+  // SM keep their gathers in flight.  With one CTA per 16 spans instead, the whole SM drains and refills at every
+  // CTA boundary (200 KB of shared memory: one resident CTA), which is what made short spans slow.
+  const int span_stride = (int)gridDim.x * warps_per_cta;
+  for (int si = blockIdx.x * warps_per_cta + warp; si < n_spans; si += span_stride) {
+  const int4 spv = __ldg(reinterpret_cast<const int4*>(spans) + si);
+  const int v_beg = spv.x, v_end = spv.y, f4_beg = spv.z, f4_cnt = spv.w;
 
   bool cv[VPLMAX];
 #pragma unroll
@@ -284,6 +290,7 @@ __device__ __forceinline__ void spmm_stream_body(const SpmmArgs& a, const Stream
     }
   }
   while (v < v_end) flush_row();                         // spans made of empty rows only
+  }   // next span of this warp
 }
 
 template <int VPLMAX, int D, int WARPS, int MINB, bool SMEM, int LEAN>
@@ -306,7 +313,9 @@ static cudaError_t launch_stream_epi(const SpmmArgs& a, const StreamSchedule& s,
       attr_set = true;
     }
   }
-  const unsigned grid = (unsigned)ceil_div(s.n_spans, WARPS);
+  unsigned grid = (unsigned)ceil_div(s.n_spans, WARPS);
+  static const int persistent = getenv("GCG_STREAM_PERSISTENT") ? atoi(getenv("GCG_STREAM_PERSISTENT")) : kStreamPersistent;
+  if (persistent) grid = std::min<unsigned>(grid, (unsigned)(kNumSMs * MINB));
   const int near = g_stream_near >= 0 ? g_stream_near : ss.near_window;
   kern<<<grid, WARPS * 32, smem_bytes, st>>>(a, s.d_spans, s.n_spans, ss.d_vptr, ss.d_vdst, (int)ss.n_v, near);
   return cudaGetLastError();
