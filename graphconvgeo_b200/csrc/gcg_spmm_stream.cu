@@ -40,6 +40,7 @@ struct StreamState {
   int64_t n_v = 0;
   int32_t* d_vptr = nullptr;            // [n_v + 1]
   int32_t* d_vdst = nullptr;            // [n_v]
+  int32_t* d_cursor = nullptr;          // next span to hand out (persistent grid with dynamic span distribution)
   std::vector<int32_t> h_vptr;          // host copies
   std::vector<int32_t> h_row_v;         // [n_rows + 1] first virtual row of every row
   std::vector<int32_t> blk_rows;        // [n_blocks + 1] row ranges of the schedule (empty = one block)
@@ -63,6 +64,7 @@ void stream_state_destroy(StreamState* s) {
   if (!s) return;
   if (s->d_vptr) cudaFree(s->d_vptr);
   if (s->d_vdst) cudaFree(s->d_vdst);
+  if (s->d_cursor) cudaFree(s->d_cursor);
   for (auto& kv : s->scheds)
     if (kv.second.d_spans) cudaFree(kv.second.d_spans);
   delete s;
@@ -141,7 +143,7 @@ __device__ __forceinline__ void epilogue_store_gate(const SpmmArgs& a, int64_t r
 template <int VPLMAX, int D, bool SMEM, int LEAN>
 __device__ __forceinline__ void spmm_stream_body(const SpmmArgs& a, const StreamSpan* __restrict__ spans, int n_spans,
                                                  const int* __restrict__ vptr, const int* __restrict__ vdst, int n_v,
-                                                 int warps_per_cta, int near_window) {
+                                                 int warps_per_cta, int near_window, int* __restrict__ cursor) {
   extern __shared__ __align__(128) uint8_t smem_dyn[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint64_t keep = policy_evict_last(), strm = policy_evict_first();
@@ -151,8 +153,18 @@ __device__ __forceinline__ void spmm_stream_body(const SpmmArgs& a, const Stream
   // window of the schedule -- but a warp that finishes a span starts its next one while the other 15 warps of the
   // SM keep their gathers in flight.  With one CTA per 16 spans instead, the whole SM drains and refills at every
   // CTA boundary (200 KB of shared memory: one resident CTA), which is what made short spans slow.
+  // `cursor` != nullptr: spans are handed out in order by an atomic counter instead (dynamic: a warp that finishes
+  // takes the NEXT span of the matrix, so the spans in flight stay consecutive however unevenly the warps advance;
+  // with the static stride the warps drift apart and the window widens -- measured 9.6 vs 8.4 ms).
   const int span_stride = (int)gridDim.x * warps_per_cta;
-  for (int si = blockIdx.x * warps_per_cta + warp; si < n_spans; si += span_stride) {
+  int si = blockIdx.x * warps_per_cta + warp;
+  for (;; si += span_stride) {
+    if (cursor) {
+      int nx = 0;
+      if (lane == 0) nx = atomicAdd(cursor, 1);
+      si = __shfl_sync(full, nx, 0);
+    }
+    if (si >= n_spans) break;
   const int4 spv = __ldg(reinterpret_cast<const int4*>(spans) + si);
   const int v_beg = spv.x, v_end = spv.y, f4_beg = spv.z, f4_cnt = spv.w;
 
@@ -296,8 +308,8 @@ __device__ __forceinline__ void spmm_stream_body(const SpmmArgs& a, const Stream
 template <int VPLMAX, int D, int WARPS, int MINB, bool SMEM, int LEAN>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 spmm_stream_kernel(const SpmmArgs a, const StreamSpan* __restrict__ spans, int n_spans, const int* __restrict__ vptr,
-                   const int* __restrict__ vdst, int n_v, int near_window) {
-  spmm_stream_body<VPLMAX, D, SMEM, LEAN>(a, spans, n_spans, vptr, vdst, n_v, WARPS, near_window);
+                   const int* __restrict__ vdst, int n_v, int near_window, int* __restrict__ cursor) {
+  spmm_stream_body<VPLMAX, D, SMEM, LEAN>(a, spans, n_spans, vptr, vdst, n_v, WARPS, near_window, cursor);
 }
 
 // ------------------------------------------------------------------------------------------ host side
@@ -314,10 +326,19 @@ static cudaError_t launch_stream_epi(const SpmmArgs& a, const StreamSchedule& s,
     }
   }
   unsigned grid = (unsigned)ceil_div(s.n_spans, WARPS);
+  // 0: one CTA per 16 spans; 1: persistent grid, static stride; 2: persistent grid, spans handed out by an atomic cursor
   static const int persistent = getenv("GCG_STREAM_PERSISTENT") ? atoi(getenv("GCG_STREAM_PERSISTENT")) : kStreamPersistent;
-  if (persistent) grid = std::min<unsigned>(grid, (unsigned)(kNumSMs * MINB));
+  int* cursor = nullptr;
+  if (persistent && grid > (unsigned)(kNumSMs * MINB)) {
+    grid = (unsigned)(kNumSMs * MINB);
+    if (persistent == 2 && ss.d_cursor) {
+      cursor = ss.d_cursor;
+      cudaError_t e = cudaMemsetAsync(cursor, 0, sizeof(int32_t), st);
+      if (e != cudaSuccess) return e;
+    }
+  }
   const int near = g_stream_near >= 0 ? g_stream_near : ss.near_window;
-  kern<<<grid, WARPS * 32, smem_bytes, st>>>(a, s.d_spans, s.n_spans, ss.d_vptr, ss.d_vdst, (int)ss.n_v, near);
+  kern<<<grid, WARPS * 32, smem_bytes, st>>>(a, s.d_spans, s.n_spans, ss.d_vptr, ss.d_vdst, (int)ss.n_v, near, cursor);
   return cudaGetLastError();
 }
 
@@ -394,6 +415,7 @@ static int build_vrows(const gcg_plan* p, StreamState* s) {
   if (seg != p->n_seg) { set_error("stream plan: segment count mismatch (%d vs %lld)", seg, (long long)p->n_seg); return GCG_ERR_SHAPE; }
   GCG_CUDA(cudaMalloc(&s->d_vptr, sizeof(int32_t) * (s->n_v + 1)));
   GCG_CUDA(cudaMalloc(&s->d_vdst, sizeof(int32_t) * std::max<int64_t>(1, s->n_v)));
+  GCG_CUDA(cudaMalloc(&s->d_cursor, sizeof(int32_t)));
   GCG_CUDA(cudaMemcpy(s->d_vptr, s->h_vptr.data(), sizeof(int32_t) * (s->n_v + 1), cudaMemcpyHostToDevice));
   if (s->n_v > 0) GCG_CUDA(cudaMemcpy(s->d_vdst, vdst.data(), sizeof(int32_t) * s->n_v, cudaMemcpyHostToDevice));
   return GCG_OK;
