@@ -157,23 +157,38 @@ __device__ __forceinline__ void spmm_stream_body(const SpmmArgs& a, const Stream
   // takes the NEXT span of the matrix, so the spans in flight stay consecutive however unevenly the warps advance;
   // with the static stride the warps drift apart and the window widens -- measured 9.6 vs 8.4 ms).
   const int span_stride = (int)gridDim.x * warps_per_cta;
+  // the next span of this warp: its index (cursor or stride), descriptor and non-zero range.  Fetched while the
+  // CURRENT span drains (its last D - 1 gathers are in flight anyway), so that a new span starts with one level of
+  // dependent loads (its first index / value / row-boundary chunks) instead of four.
   int si = blockIdx.x * warps_per_cta + warp;
-  for (;; si += span_stride) {
+  int4 spv_n = make_int4(0, 0, 0, 0);
+  int k0_n = 0, k1_n = 0;
+  auto fetch_next = [&](bool first) {
     if (cursor) {
       int nx = 0;
       if (lane == 0) nx = atomicAdd(cursor, 1);
       si = __shfl_sync(full, nx, 0);
+    } else if (!first) {
+      si += span_stride;
     }
-    if (si >= n_spans) break;
-  const int4 spv = __ldg(reinterpret_cast<const int4*>(spans) + si);
+    if (si < n_spans) {
+      spv_n = __ldg(reinterpret_cast<const int4*>(spans) + si);
+      k0_n = __ldg(vptr + spv_n.x);
+      k1_n = __ldg(vptr + spv_n.y);
+    }
+  };
+  fetch_next(true);
+  while (si < n_spans) {
+  const int4 spv = spv_n;
   const int v_beg = spv.x, v_end = spv.y, f4_beg = spv.z, f4_cnt = spv.w;
+  bool fetched = false;
 
   bool cv[VPLMAX];
 #pragma unroll
   for (int j = 0; j < VPLMAX; ++j) cv[j] = (lane + 32 * j) < f4_cnt;
   const float4* __restrict__ Bp = reinterpret_cast<const float4*>(a.B) + f4_beg + lane;
   const int64_t ldb4 = a.ldb >> 2;
-  const int k0 = __ldg(vptr + v_beg), k1 = __ldg(vptr + v_end);
+  const int k0 = k0_n, k1 = k1_n;
   const int nnz_total = a.nnz_total;
 
   // chunk caches: 32 consecutive column indices (producer side), values (consumer side) and virtual-row
@@ -241,6 +256,7 @@ __device__ __forceinline__ void spmm_stream_body(const SpmmArgs& a, const Stream
     const uint32_t ring = smem_u32(smem_dyn) + (uint32_t)warp * (D * SLOT) + lane * 16;
     uint32_t ps = 0, cs = (D > 1) ? SLOT : 0;          // producer slot offset; consumer runs one slot ahead of it
     for (int t = k0; t < k1 + D; ++t) {
+      if (t == k1) { fetch_next(false); fetched = true; }     // first drain iteration: see fetch_next
       if (t < k1) {
         if (t >= pb + 32) { pb += 32; pidx = pidx_nx; pidx_nx = ld_idx(pb + 32); }
         const int col = __shfl_sync(full, pidx, t - pb);
@@ -302,6 +318,7 @@ __device__ __forceinline__ void spmm_stream_body(const SpmmArgs& a, const Stream
     }
   }
   while (v < v_end) flush_row();                         // spans made of empty rows only
+  if (!fetched) fetch_next(false);                       // register-pipeline variants
   }   // next span of this warp
 }
 
