@@ -51,13 +51,20 @@ struct StreamState {
 
 static int g_stream_variant = 0;     // 0 = auto
 static int g_stream_span_nnz = 0;    // 0 = default
-// Non-zeros per span (= per warp).  All 148 x 16 warps advance together, so the rows whose neighbourhoods compete for
-// L2 at any moment are the span length times 2,368: SHORT spans keep that window narrow.  An LRU model of the benched
-// graph (scripts/l2_model.py, profiles/r02_l2_model.json) reproduces the measured traffic at 256 (47.7 GB modelled,
-// 49.6 GB measured) and at 384 (51.9 GB; 8.30 vs 7.65 ms measured = the same ratio) and predicts 42 / 38.7 GB at
-// 128 / 64; the per-span start-up (two dependent loads + 4 pipeline-fill iterations) bounds it from below.
-constexpr int kDefaultSpanNnz = 384;
-constexpr int kStreamPersistent = 0;   // 1: one CTA per SM, warps loop over the spans (see spmm_stream_body)
+// Non-zeros per span (= per warp) and how spans reach the warps.  All 148 x 16 warps advance together, so the rows
+// whose neighbourhoods compete for L2 at any moment are the span length times 2,368: SHORT spans keep that window
+// narrow.  An LRU model of the benched graph (scripts/l2_model.py, profiles/r02_l2_model.json) reproduces the
+// measured traffic at 256 non-zeros per span (47.7 GB modelled, 49.6 GB measured) and at 384 (51.9 GB; 8.30 vs
+// 7.65 ms measured = the same ratio) and predicts 42 / 38.7 GB at 128 / 64.  Measured (profiles/r02_spmm_spans.md):
+//   * one CTA per 16 spans (round-2 default until the last day): shorter spans LOSE (8.39 ms at 384, 9.42 at 64) --
+//     200 KB of shared memory means one resident CTA, so the SM drains and refills at every CTA boundary;
+//   * persistent grid, static stride over the spans: 9.6 ms -- the warps drift apart and the window widens;
+//   * persistent grid, spans handed out IN ORDER by an atomic cursor, next span's descriptor fetched while the
+//     current one drains: 8.30 ms at 128 against 8.85 ms for the old default on the same box, X^T.dZ1's block-major
+//     matrix 18.8 -> 15.2 ms, epoch 209.2 -> 203.3 ms.  Below 128 the per-span start-up wins again, and at
+//     ~8.4 TB/s of gathered bytes the kernel is now near the L2 -> SM rate rather than the DRAM rate.
+constexpr int kDefaultSpanNnz = 128;
+constexpr int kStreamPersistent = 2;   // 0: one CTA per 16 spans; 1: persistent, static stride; 2: persistent, cursor
 static int g_stream_near = -1;       // -1 = plan's own choice, 0 = every gather evict_last, > 0 = window in rows
 
 void stream_state_destroy(StreamState* s) {
