@@ -173,3 +173,27 @@ def test_training_reduces_loss():
     net = go.GCNOracle(X, A, 3, True, (1e-6, 1e-6))
     hist = go.train_epochs(net, params, idx, y, 40)
     assert hist[-1][0] < hist[0][0] - 0.02
+
+
+def test_sampled_parity_report_bound_and_reference_noise_floor():
+    """oracle/sampled_parity._Report: the scaled error is |got - ref| / (1e-6 + 1e-4|ref|); a check that carries the
+    reference's own float32 result is also measured against that result's distance from the float64 values."""
+    import numpy as np
+    from oracle.sampled_parity import _Report
+    rep = _Report()
+    ref = np.array([0.0, 1.0, -100.0])
+    assert rep.add("exact", ref.copy(), ref) == 0.0
+    got = ref + np.array([5e-7, 5e-5, 0.0])             # half the absolute term, half the relative term
+    assert abs(rep.add("half", got, ref) - 0.5) < 0.01
+    r = rep.add("over with floor", ref + np.array([2e-6, 0, 0]), ref, reference_f32=ref + np.array([3e-6, 0, 0]))
+    assert abs(r - 2.0) < 1e-9
+    s = rep.summary()
+    assert s["worst_check"] == "over with floor" and abs(s["max_scaled_err"] - 2.0) < 1e-9
+    fl = s["reference_f32_noise"]["over with floor"]
+    assert abs(fl["max_scaled_err"] - 3.0) < 1e-9 and abs(fl["gpu_vs_reference_f32"] - 1.0) < 1e-6
+    # 2.0 against a floor of 3.0: inside the reference's own noise -> excess < 1; "half" has no floor -> 0.5
+    assert abs(s["max_scaled_err_over_reference_noise"] - 2.0 / 3.0) < 1e-9
+    rep.add("over without floor", ref + np.array([4e-6, 0, 0]), ref)
+    s = rep.summary()
+    assert s["worst_check_over_reference_noise"] == "over without floor" and abs(s["max_scaled_err_over_reference_noise"] - 4.0) < 1e-9
+    assert s["checks"]["over without floor"]["frac_over"] == 1.0 / 3.0
