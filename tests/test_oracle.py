@@ -190,7 +190,7 @@ def test_sampled_parity_report_bound_and_reference_noise_floor():
     s = rep.summary()
     assert s["worst_check"] == "over with floor" and abs(s["max_scaled_err"] - 2.0) < 1e-9
     fl = s["reference_f32_noise"]["over with floor"]
-    assert abs(fl["max_scaled_err"] - 3.0) < 1e-9 and abs(fl["gpu_vs_reference_f32"] - 1.0) < 1e-6
+    assert abs(fl["max_scaled_err"] - 3.0) < 1e-9 and abs(fl["gpu_vs_reference_f32"] - 1.0) < 1e-3
     # 2.0 against a floor of 3.0: inside the reference's own noise -> excess < 1; "half" has no floor -> 0.5
     assert abs(s["max_scaled_err_over_reference_noise"] - 2.0 / 3.0) < 1e-9
     rep.add("over without floor", ref + np.array([4e-6, 0, 0]), ref)
