@@ -746,7 +746,9 @@ def spmm_roofline(m, wl, dev, reps=10):
     gather_model = (8 * nnz + 4 * nnz * F + 4 * N * F) / (t_ms * 1e-3) / 1e9
     return {"roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "kernel": "%s (A_hat.H, F=%d%s)" % (
-                             "spmm_stream_kernel" if ops.auto_panel_cols(n_in, F, nnz) == -2 else "spmm_vec_kernel", F,
+                             "spmm_stream_kernel" if ops.auto_panel_cols(
+                                 n_in, ((-(-F // A.part.world) + 3) // 4 * 4) if hasattr(A, "full") else F, nnz) == -2
+                             else "spmm_vec_kernel", F,
                              (", this rank's share: %s" % ("all rows x F/P columns incl. the two peer-store transposes"
                                                             if hasattr(A, "full") else "local rows incl. NCCL all-gather of H"))
                              if dist_mode else ""),
