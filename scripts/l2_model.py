@@ -24,7 +24,7 @@ sys.path.insert(0, ROOT)
 
 
 def lru_lib():
-    so = "/tmp/gcg_l2_lru.so"
+    so = os.path.join(ROOT, "scripts", "_l2_lru.so")        # git-ignored (*.so)
     src = os.path.join(ROOT, "scripts", "l2_lru.c")
     if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
         subprocess.check_call(["gcc", "-O2", "-shared", "-fPIC", "-o", so, src])
